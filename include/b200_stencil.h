@@ -1,0 +1,158 @@
+/*
+ * b200_stencil.h -- C ABI of libb200stencil.so: the B200 (sm_100a) target for the
+ * kernelgen-perf-tests stencil hot path.
+ *
+ * This is the drop-in boundary.  Everything a `b200` per-test driver (the
+ * replacement for main() in <test>/<test>.c of the reference) needs is here:
+ * plain C, plain pointers and sizes, int return codes (0 = ok; the message is
+ * in b200_last_error()).  No CUDA or torch types appear in any signature;
+ * streams are passed as void* (a cudaStream_t, NULL = default stream).
+ *
+ * Two layers:
+ *
+ *  (1) Sweep launch API -- stateless: one sweep of one test over caller-owned
+ *      DEVICE buffers.  Replaces the kernel call site of the reference:
+ *        CPU   laplacian(nx, ny, ns, alpha, beta, w0p, w1p)         laplacian/laplacian.c:290
+ *        CUDA  laplacian<<<grid,block,shmem>>>(nx,ny,ns,config,...)  laplacian/laplacian.c:292-295
+ *      plus kernelgen_cuda_configure_gird()                           <test>/cuda/cuda_profiling.cu:36-111
+ *      (launch geometry is planned inside the library).
+ *
+ *  (2) Context API -- what the reference's cuda-target driver does around the
+ *      kernel, phase by phase, so the driver can print the same timing lines:
+ *        b200_init   <-> cudaGetDeviceCount probe      laplacian/laplacian.c:192-199  ("init time")
+ *        b200_plan + b200_alloc <-> cudaMalloc xN      laplacian/laplacian.c:223-231  ("device buffer alloc time")
+ *        b200_load   <-> cudaMemcpy H2D                laplacian/laplacian.c:255-262  ("data load time")
+ *        b200_run    <-> the nt-loop with swap         laplacian/laplacian.c:287-301  ("compute time")
+ *        b200_result_slot <-> idxs remap               laplacian/laplacian.c:307-313
+ *        b200_save   <-> cudaMemcpy D2H                laplacian/laplacian.c:334-340  ("data save time")
+ *        b200_free   <-> cudaFree xN                   laplacian/laplacian.c:362-369  ("device buffer free time")
+ *      and the per-launch profiler lines ("<k> regcount = N", "<k> kernel time = T")
+ *      of __wrap_cudaLaunchKernel, <test>/cuda/cuda_profiling.cu:214-251, are
+ *      served by b200_stats.
+ *
+ * Array order ("slots") for every test is the reference driver's init order:
+ *   laplacian w0,w1 | wave13pt w0,w1,w2 | divergence u,ux,uy,uz | gradient u,ux,uy,uz |
+ *   uxx1 u0,u1,d1,xx,xy,xz | lapgsrb w0,w1 | jacobi w0,w1 | gaussblur w0,w1 |
+ *   gameoflife u0,u1 | tricubic,tricubic2 u0,u1,a,b,c | vecadd w0,w1,w2 |
+ *   matvec A,x,y | sincos x,y,xy
+ * Layout: x fastest, index = i + nx*(j + ny*k).  2D tests use (nx, ny), ns = 1.
+ *
+ * There is NO CPU fallback: every entry point that computes fails with
+ * B200_ERR_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef B200_STENCIL_H
+#define B200_STENCIL_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_API_VERSION 1
+
+typedef enum {
+    B200_LAPLACIAN = 0, B200_WAVE13PT, B200_DIVERGENCE, B200_GRADIENT, B200_UXX1,
+    B200_LAPGSRB, B200_JACOBI, B200_GAUSSBLUR, B200_GAMEOFLIFE, B200_TRICUBIC,
+    B200_TRICUBIC2, B200_VECADD, B200_MATVEC, B200_SINCOS, B200_NTESTS
+} b200_test_t;
+
+typedef enum { B200_F32 = 0, B200_F64 = 1 } b200_dtype_t;
+
+enum {
+    B200_OK = 0,
+    B200_ERR_ARG = 1,        /* bad argument (sizes, ids, NULL) */
+    B200_ERR_CUDA = 2,       /* a CUDA runtime/driver call failed */
+    B200_ERR_NO_DEVICE = 3,  /* no usable sm_100 device: there is no CPU fallback */
+    B200_ERR_STATE = 4,      /* context call out of order */
+    B200_ERR_NOMEM = 5
+};
+
+#define B200_MAX_ARRAYS 8
+#define B200_MAX_SCALARS 8
+
+/* Static description of a test (mirrors what each reference driver hard-codes). */
+typedef struct {
+    const char* name;      /* "laplacian", ... == directory / kernel name in the suite */
+    int ndims;             /* 3: <nx> <ny> <ns> <nt>;  2: <nx> <ny> <nt> */
+    int narrays;           /* arrays, in driver init order */
+    int nscalars;          /* rand()-drawn coefficients */
+    int rotation;          /* 0 none; 2 swap slots 0,1 per sweep; 3 rotate slots 0,1,2 */
+    int lo[3], hi[3];      /* interior: lo[d] <= idx < n[d]-hi[d]  (x,y,z) */
+    int nread, nwritten;   /* arrays touched per sweep -> algorithmic bytes/LUP = (nread+nwritten)*sizeof(real) */
+    int zghost_lo, zghost_hi; /* ghost depth needed below/above in the slab-split dimension (z; y for 2D) */
+    int exchange_slot;     /* slot whose ghost planes must be refreshed after each sweep (-1: none) */
+} b200_test_info;
+
+const b200_test_info* b200_get_test_info(int test);
+int b200_test_by_name(const char* name);            /* -1 if unknown */
+const char* b200_last_error(void);
+int b200_api_version(void);
+
+/* Interior lattice-point updates per sweep for the given extents (0 if degenerate). */
+unsigned long long b200_interior_points(int test, int nx, int ny, int ns);
+
+/* ---- device / environment ------------------------------------------------ */
+int b200_device_count(int* count);                  /* usable sm_100 devices */
+
+/* ---- (1) sweep launch API ------------------------------------------------ */
+typedef struct {
+    int test;                       /* b200_test_t */
+    int dtype;                      /* b200_dtype_t */
+    int nx, ny, ns;                 /* extents of the arrays as laid out in memory (a z-slab incl. ghosts) */
+    double scalars[B200_MAX_SCALARS];
+    /* Output range in the slab-split dimension (z for 3D tests, y for 2D tests),
+     * in local array coordinates, half-open.  Must lie inside the interior.
+     * out_begin == out_end == 0 selects the whole interior. */
+    int out_begin, out_end;
+    /* Fused halo push (multi-GPU): optional peer-mapped pointers to the lower /
+     * upper neighbour's copy of the OUTPUT array (same layout, the neighbour's
+     * local coordinates).  The kernel stores the planes the neighbour needs as
+     * ghosts directly into peer memory over NVLink while it computes.
+     * push_lo_dst_plane: first ghost plane index in the lower neighbour that
+     * receives our planes [push_lo_src_plane, +zghost_hi); likewise for hi. */
+    void* push_lo; int push_lo_src_plane; int push_lo_dst_plane; int push_lo_count;
+    void* push_hi; int push_hi_src_plane; int push_hi_dst_plane; int push_hi_count;
+} b200_sweep_desc;
+
+/* One sweep: arrays[] are DEVICE pointers in slot order (current rotation
+ * already applied by the caller).  Asynchronous on `stream`. */
+int b200_sweep(const b200_sweep_desc* desc, void* const* arrays, void* stream);
+
+/* Registers per thread / kernel symbol of the kernel b200_sweep would launch. */
+int b200_kernel_info(int test, int dtype, int* regs_per_thread, const char** kernel_name);
+
+/* Number of kernel launches issued by this library since load (for gpu_launches). */
+unsigned long long b200_launch_count(void);
+
+/* ---- (2) context API ----------------------------------------------------- */
+typedef struct b200_ctx b200_ctx;
+
+typedef struct {
+    double kernel_ms_per_sweep;     /* CUDA-event time of the nt-loop / nt */
+    double kernel_ms_total;
+    int regs_per_thread;
+    int launches;                   /* kernel launches issued by b200_run */
+    const char* kernel_name;
+    int ngpus;
+} b200_stats;
+
+int b200_init(b200_ctx** ctx, int ngpus);           /* ngpus <= 0: env B200_NGPUS or 1 */
+int b200_plan(b200_ctx* ctx, int test, int dtype, int nx, int ny, int ns,
+              const double* scalars, int nscalars);
+int b200_alloc(b200_ctx* ctx);
+int b200_load(b200_ctx* ctx, int slot, const void* host);
+int b200_run(b200_ctx* ctx, int niters, b200_stats* stats);
+int b200_result_slot(const b200_ctx* ctx);          /* slot (original numbering) the reference reports f_mean on */
+int b200_save(b200_ctx* ctx, int slot, void* host);
+int b200_free(b200_ctx* ctx);                       /* releases device buffers; ctx stays valid for re-plan */
+int b200_destroy(b200_ctx* ctx);
+
+/* Pinned host staging buffers (so t_load/t_save and the e2e bench run at PCIe rate). */
+int b200_host_alloc(void** ptr, size_t bytes);
+int b200_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_STENCIL_H */

@@ -1,0 +1,166 @@
+// b200_launch.cuh -- host-side launch planning for the tile-streaming engine.
+//
+// Replaces kernelgen_cuda_configure_gird (<test>/cuda/cuda_profiling.cu:36-111 of the
+// reference): instead of "128x1x1 blocks, one thread per point" the plan is
+//   x tiles of TX, y tiles of TY over the interior, z cut into nzc chunks,
+//   grid = min(items, SMs * resident CTAs per SM)  (persistent CTAs),
+// with nzc chosen so that the items fill whole rounds of the grid (tail effect) while the
+// z-chunks stay long enough to amortise the WARM warm-up planes of the z-march.
+#pragma once
+
+#include <mutex>
+
+#include "b200_internal.h"
+#include "b200_stream.cuh"
+
+namespace b200 {
+
+template <class Op> struct KernelSetup {
+    bool done[16] = {};
+    int blocks_per_sm[16] = {};
+    std::mutex mu;
+    int get(int device, int* bps)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (device < 0 || device >= 16) { set_error("device index %d out of range", device); return B200_ERR_ARG; }
+        if (!done[device]) {
+            B200_CUDA(cudaFuncSetAttribute(stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Geo<Op>::SMEM_BYTES));
+            int n = 0;
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stream_kernel<Op>, NTHREADS,
+                                                                    Geo<Op>::SMEM_BYTES));
+            if (n < 1) { set_error("kernel does not fit on an SM"); return B200_ERR_CUDA; }
+            blocks_per_sm[device] = n;
+            done[device] = true;
+        }
+        *bps = blocks_per_sm[device];
+        return B200_OK;
+    }
+};
+
+template <class Op> KernelSetup<Op>& kernel_setup()
+{
+    static KernelSetup<Op> s;
+    return s;
+}
+
+// Pick the number of z-chunks: maximise (grid fill of the last round) x (1 - warm-up overhead).
+inline void plan_zchunks(int tiles_xy, int nz, int warm, int grid_cap, int* nzc_out, int* len_out)
+{
+    int best = 1;
+    double best_score = -1.0;
+    const int max_chunks = nz;      // chunk length >= 1
+    for (int nzc = 1; nzc <= max_chunks; nzc++) {
+        const int len = (nz + nzc - 1) / nzc;
+        const int real_nzc = (nz + len - 1) / len;
+        if (real_nzc != nzc) continue;
+        const long long items = (long long)tiles_xy * nzc;
+        const long long rounds = (items + grid_cap - 1) / grid_cap;
+        const double fill = (double)items / (double)(rounds * grid_cap);
+        const double work = (double)len / (double)(len + warm);
+        const double score = fill * work;
+        if (score > best_score + 1e-9) { best_score = score; best = nzc; }
+        if (len <= 4) break;
+    }
+    *nzc_out = best;
+    *len_out = (nz + best - 1) / best;
+}
+
+template <class Op> int launch_stream(const HostArgs& a)
+{
+    using T = typename Op::real;
+    using G = Geo<Op>;
+    const b200_sweep_desc& d = *a.desc;
+    const b200_test_info* ti = b200_get_test_info(d.test);
+
+    int bps = 0;
+    if (int rc = kernel_setup<Op>().get(a.device, &bps)) return rc;
+
+    StreamParams P{};
+    TensorMaps M{};
+    P.nx = d.nx; P.ny = d.ny; P.ns = (ti->ndims == 3) ? d.ns : 1;
+    P.xlo = ti->lo[0]; P.xhi = P.nx - ti->hi[0];
+    P.ylo = ti->lo[1]; P.yhi = P.ny - ti->hi[1];
+    if (ti->ndims == 3) { P.z0 = ti->lo[2]; P.z1 = P.ns - ti->hi[2]; }
+    else                { P.z0 = 0; P.z1 = 1; }
+    if (d.out_begin != 0 || d.out_end != 0) {
+        int& lo = (ti->ndims == 3) ? P.z0 : P.ylo;
+        int& hi = (ti->ndims == 3) ? P.z1 : P.yhi;
+        if (d.out_begin < lo || d.out_end > hi || d.out_begin > d.out_end) {
+            set_error("%s: output range [%d,%d) outside the interior [%d,%d)", ti->name, d.out_begin, d.out_end, lo, hi);
+            return B200_ERR_ARG;
+        }
+        lo = d.out_begin; hi = d.out_end;
+    }
+    if (P.xhi <= P.xlo || P.yhi <= P.ylo || P.z1 <= P.z0) return B200_OK;   // empty interior: nothing to update
+
+    const size_t pitch = (size_t)P.nx * sizeof(T);
+    bool aligned = (pitch % 16) == 0;
+    for (int q = 0; q < ti->narrays; q++) {
+        if (!a.arrays[q]) { set_error("%s: array slot %d is NULL", ti->name, q); return B200_ERR_ARG; }
+        P.arr[q] = a.arrays[q];
+        if (((uintptr_t)a.arrays[q]) % 16) aligned = false;
+    }
+    for (int q = 0; q < B200_MAX_SCALARS; q++) P.sc[q] = d.scalars[q];
+    static const bool no_tma = getenv("B200_NO_TMA") != nullptr;
+    P.use_tma = aligned && !no_tma;
+    P.vec_ok = aligned;
+
+    P.push_slot = -1;
+    P.push_dim = ti->ndims == 3 ? 2 : 1;
+    if (d.push_lo || d.push_hi) {
+        if (ti->exchange_slot < 0) { set_error("%s has no exchanged array", ti->name); return B200_ERR_ARG; }
+        // the array being written this sweep is the last slot of the rotation (slot 1 or 2)
+        P.push_slot = (ti->rotation == 3) ? 2 : 1;
+        P.push_lo = d.push_lo; P.push_lo_src = d.push_lo_src_plane; P.push_lo_dst = d.push_lo_dst_plane; P.push_lo_cnt = d.push_lo_count;
+        P.push_hi = d.push_hi; P.push_hi_src = d.push_hi_src_plane; P.push_hi_dst = d.push_hi_dst_plane; P.push_hi_cnt = d.push_hi_count;
+        if (((uintptr_t)d.push_lo) % 16 || ((uintptr_t)d.push_hi) % 16) P.vec_ok = 0;
+    }
+
+    P.ntx = (P.nx + Op::TX - 1) / Op::TX;
+    P.nty = (P.yhi - P.ylo + Op::TY - 1) / Op::TY;
+    const int grid_cap = a.num_sms * bps;
+    plan_zchunks(P.ntx * P.nty, P.z1 - P.z0, Op::WARM, grid_cap, &P.nzc, &P.zc_len);
+    const long long items = (long long)P.ntx * P.nty * P.nzc;
+    if (items > 0x7fffffffLL) { set_error("grid too large"); return B200_ERR_ARG; }
+    P.nitems = (int)items;
+
+    if (P.use_tma) {
+        for (int s = 0; s < Op::NSTAGED; s++) {
+            TmaBoxKey key{P.arr[Op::spec(s).slot], P.nx, P.ny, P.ns, (int)sizeof(T), G::bw(s), G::bh(s)};
+            if (int rc = get_tensor_map(key, &M.m[s])) return rc;
+        }
+    }
+
+    const int grid = (int)(items < grid_cap ? items : grid_cap);
+    stream_kernel<Op><<<grid, NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+    return B200_OK;
+}
+
+template <class Op> int info_stream(KernelInfo* ki, const char* name)
+{
+    cudaFuncAttributes fa;
+    B200_CUDA(cudaFuncGetAttributes(&fa, stream_kernel<Op>));
+    ki->regs = fa.numRegs;
+    ki->smem_bytes = Geo<Op>::SMEM_BYTES;
+    ki->name = name;
+    int dev = 0, bps = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    if (int rc = kernel_setup<Op>().get(dev, &bps)) return rc;
+    ki->blocks_per_sm = bps;
+    return B200_OK;
+}
+
+#define B200_DEFINE_OP(name, OpT)                                                              \
+    int launch_##name(int dtype, const HostArgs& a)                                            \
+    {                                                                                          \
+        return dtype == B200_F32 ? launch_stream<OpT<float>>(a) : launch_stream<OpT<double>>(a); \
+    }                                                                                          \
+    int info_##name(int dtype, KernelInfo* ki)                                                 \
+    {                                                                                          \
+        return dtype == B200_F32 ? info_stream<OpT<float>>(ki, #name) : info_stream<OpT<double>>(ki, #name); \
+    }
+
+}  // namespace b200

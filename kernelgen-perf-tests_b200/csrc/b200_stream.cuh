@@ -1,0 +1,318 @@
+// b200_stream.cuh -- the tile-streaming stencil engine for sm_100a.
+//
+// One persistent, warp-specialised kernel template drives every stencil:
+//
+//   * the grid is cut into work items (x-tile, y-tile, z-chunk); CTA b takes
+//     items b, b+grid, ... so that CTAs resident at the same time work on
+//     neighbouring tiles (their halo overlap is then an L2 hit, not HBM);
+//   * a producer warp walks the item's planes and brings one plane-tile of
+//     every staged input (with its x/y halo) into a shared-memory ring with
+//     TMA (cp.async.bulk.tensor.3d + mbarrier complete_tx); out-of-range
+//     halo is zero-filled by the TMA unit;
+//   * 8 consumer warps wait on the stage's "full" mbarrier, run Op::step()
+//     -- the stencil proper: in-plane neighbours from shared memory with
+//     16-byte loads, z neighbours from per-thread register queues (2.5D
+//     z-march) -- store results with 16-byte coalesced stores and hand the
+//     stage back through the "empty" mbarrier;
+//   * optional fused halo push: planes a z-neighbour GPU needs as ghosts are
+//     also stored straight into that GPU's memory (peer pointer over NVLink).
+//
+// When a row pitch is not a multiple of 16 bytes TMA cannot be used; the
+// producer warp then fills the same ring with bounds-checked scalar loads.
+#pragma once
+
+#include "b200_common.cuh"
+
+namespace b200 {
+
+constexpr int NCONS = 256;              // consumer threads (8 warps)
+constexpr int NTHREADS = NCONS + 32;    // + 1 producer warp
+constexpr int MAX_STAGED = 5;
+constexpr int MAX_STAGES = 8;           // 2*MAX_STAGES mbarriers fit the 128-byte header
+
+// One staged (TMA-loaded) input of an Op.
+struct StagedSpec {
+    int slot;   // array slot (driver order) it is loaded from
+    int hx;     // 1: tile carries an x halo of V elements (16 bytes) on each side
+    int ylo;    // rows of halo below / above
+    int yhi;
+    int lead;   // at the step that emits output plane s, plane s+lead of this array arrives
+    int zlo;    // deepest plane below the output plane that is needed (s - zlo)
+};
+
+struct StreamParams {
+    int nx, ny, ns;                 // array extents
+    int xlo, xhi, ylo, yhi;         // output box (half-open), x and y
+    int z0, z1;                     // output planes
+    int ntx, nty, nzc, zc_len;      // work decomposition
+    int nitems;
+    int use_tma;                    // 0: scalar fallback loader
+    int vec_ok;                     // 16-byte stores legal
+    void* arr[8];                   // device pointers, slot order
+    double sc[8];                   // scalars
+    // fused halo push of the exchanged output array
+    void* push_lo; int push_lo_src, push_lo_dst, push_lo_cnt;
+    void* push_hi; int push_hi_src, push_hi_dst, push_hi_cnt;
+    int push_slot;
+    int push_dim;                   // 2: planes (3D tests), 1: rows (2D tests)
+};
+
+struct alignas(64) TensorMaps {
+    CUtensorMap m[MAX_STAGED];
+};
+
+constexpr int round_up_c(int a, int b) { return (a + b - 1) / b * b; }
+
+// Compile-time geometry of an Op.
+template <class Op> struct Geo {
+    using T = typename Op::real;
+    static constexpr int V = 16 / (int)sizeof(T);
+    static constexpr int TX = Op::TX;
+    static constexpr int TY = Op::TY;
+    static constexpr int LX = TX / V;            // threads along x
+    static constexpr int LY = NCONS / LX;        // thread rows
+    static constexpr int CPT = TY / LY;          // rows ("columns" in z) per thread
+    static_assert(TX % V == 0 && NCONS % LX == 0 && TY % LY == 0, "bad tile");
+    static constexpr int hxp(int a) { return Op::spec(a).hx ? V : 0; }
+    static constexpr int bw(int a) { return TX + 2 * hxp(a); }
+    static constexpr int bh(int a) { return TY + Op::spec(a).ylo + Op::spec(a).yhi; }
+    static constexpr int box_bytes(int a) { return bw(a) * bh(a) * (int)sizeof(T); }
+    static constexpr int arr_bytes(int a) { return round_up_c(box_bytes(a), 128); }
+    static constexpr int arr_off(int a)
+    {
+        int o = 0;
+        for (int b = 0; b < a; b++) o += arr_bytes(b);
+        return o;
+    }
+    static constexpr int STAGE_BYTES = arr_off(Op::NSTAGED);
+    static constexpr int SMEM_BYTES = 128 /*mbarriers*/ + 128 /*alignment slack*/ + Op::STAGES * STAGE_BYTES;
+    static_assert(Op::STAGES <= MAX_STAGES && Op::NSTAGED <= MAX_STAGED, "too many stages");
+    static_assert(Op::STAGES > Op::HOLD, "ring too shallow");
+};
+
+// What Op::step() sees.
+template <class Op> struct Ctx {
+    using T = typename Op::real;
+    using G = Geo<Op>;
+    const StreamParams& P;
+    unsigned char* stages;      // base of the ring
+    uint32_t g;                 // global step counter (ring position)
+    int X0, Y0;                 // global x of tile column 0, global y of tile row 0
+    int s;                      // output plane of this step
+    int rel;                    // s - (first output plane of the item); < 0 during warm-up
+    int tx, ty;                 // consumer thread coordinates
+
+    // Pointer to this thread's 16-byte vector in tile row `row` (tile-local output row, may be
+    // negative / >= TY inside the halo) of staged array A, in the stage loaded `back` steps ago.
+    template <int A> B200_DEV const T* tile(int row, int back = 0) const
+    {
+        const uint32_t st = (g - (uint32_t)back) % (uint32_t)Op::STAGES;
+        const T* base = reinterpret_cast<const T*>(stages + st * G::STAGE_BYTES + G::arr_off(A));
+        return base + (row + Op::spec(A).ylo) * G::bw(A) + G::hxp(A) + G::V * tx;
+    }
+    B200_DEV int gx() const { return X0 + G::V * tx; }
+
+    // Read-only pointer into a global array at (x of this thread, tile row, plane).
+    template <int SLOT> B200_DEV const T* gptr(int row, int plane) const
+    {
+        const T* a = reinterpret_cast<const T*>(P.arr[SLOT]);
+        return a + ((size_t)plane * P.ny + (size_t)(Y0 + row)) * P.nx + gx();
+    }
+    // true when this thread's whole 16-byte vector at (row, any plane) is inside the array
+    B200_DEV bool vec_in_array(int row) const
+    {
+        return P.vec_ok && gx() + G::V <= P.nx && (Y0 + row) >= 0 && (Y0 + row) < P.ny;
+    }
+
+    // 16-byte (or element-predicated) store of V values at (x of this thread, y, plane) of array a
+    B200_DEV void store_vec(T* a, int y, int plane, const T (&val)[G::V]) const
+    {
+        const int x = gx();
+        T* dst = a + ((size_t)plane * P.ny + (size_t)y) * P.nx + x;
+        if (P.vec_ok && x >= P.xlo && x + G::V <= P.xhi) {
+            VReg<T> r;
+#pragma unroll
+            for (int v = 0; v < G::V; v++) r[v] = val[v];
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(r.v);
+        } else {
+#pragma unroll
+            for (int v = 0; v < G::V; v++)
+                if (x + v >= P.xlo && x + v < P.xhi) dst[v] = val[v];
+        }
+    }
+
+    // Store V results of output array SLOT at (tile row, plane); interior-predicated.
+    template <int SLOT> B200_DEV void store(int row, int plane, const T (&val)[G::V]) const
+    {
+        const int y = Y0 + row;
+        if (y < P.ylo || y >= P.yhi) return;
+        store_vec(reinterpret_cast<T*>(P.arr[SLOT]), y, plane, val);
+        if (SLOT == P.push_slot) {
+            // fused halo push: the same values also go to the neighbour GPU's ghost planes (rows for
+            // the 2D tests) through a peer-mapped pointer, i.e. over NVLink, while the sweep runs
+            const int coord = P.push_dim == 2 ? plane : y;
+            if (P.push_lo && coord >= P.push_lo_src && coord < P.push_lo_src + P.push_lo_cnt) {
+                const int d = coord - P.push_lo_src + P.push_lo_dst;
+                store_vec(reinterpret_cast<T*>(P.push_lo), P.push_dim == 2 ? y : d, P.push_dim == 2 ? d : plane, val);
+            }
+            if (P.push_hi && coord >= P.push_hi_src && coord < P.push_hi_src + P.push_hi_cnt) {
+                const int d = coord - P.push_hi_src + P.push_hi_dst;
+                store_vec(reinterpret_cast<T*>(P.push_hi), P.push_dim == 2 ? y : d, P.push_dim == 2 ? d : plane, val);
+            }
+        }
+    }
+};
+
+// Producer-side fallback: fill one staged box with bounds-checked scalar loads (zero fill outside).
+template <class Op, int A>
+B200_DEV void fallback_fill(const StreamParams& P, unsigned char* stage, int X0, int Y0, int plane, int lane)
+{
+    using G = Geo<Op>;
+    using T = typename Op::real;
+    constexpr int BW = G::bw(A), BH = G::bh(A);
+    T* dst = reinterpret_cast<T*>(stage + G::arr_off(A));
+    const T* src = reinterpret_cast<const T*>(P.arr[Op::spec(A).slot]);
+    const int gx0 = X0 - G::hxp(A), gy0 = Y0 - Op::spec(A).ylo;
+    const bool zin = plane >= 0 && plane < P.ns;
+#pragma unroll 4
+    for (int e = lane; e < BW * BH; e += 32) {
+        const int r = e / BW, c = e - r * BW;
+        const int x = gx0 + c, y = gy0 + r;
+        T v = T(0);
+        if (zin && x >= 0 && x < P.nx && y >= 0 && y < P.ny)
+            v = src[((size_t)plane * P.ny + (size_t)y) * P.nx + x];
+        dst[e] = v;
+    }
+}
+
+template <class Op, int A> struct ProducerIssue {
+    B200_DEV static void bytes(int s, int za, uint32_t& total)
+    {
+        if constexpr (A < Op::NSTAGED) {
+            if (s + Op::spec(A).lead >= za - Op::spec(A).zlo) total += Geo<Op>::box_bytes(A);
+            ProducerIssue<Op, A + 1>::bytes(s, za, total);
+        }
+    }
+    B200_DEV static void tma(const TensorMaps& M, unsigned char* stage, uint64_t* bar, int X0, int Y0, int s, int za)
+    {
+        if constexpr (A < Op::NSTAGED) {
+            if (s + Op::spec(A).lead >= za - Op::spec(A).zlo)
+                tma_load_3d(stage + Geo<Op>::arr_off(A), &M.m[A], bar, X0 - Geo<Op>::hxp(A),
+                            Y0 - Op::spec(A).ylo, s + Op::spec(A).lead);
+            ProducerIssue<Op, A + 1>::tma(M, stage, bar, X0, Y0, s, za);
+        }
+    }
+    B200_DEV static void fallback(const StreamParams& P, unsigned char* stage, int X0, int Y0, int s, int za, int lane)
+    {
+        if constexpr (A < Op::NSTAGED) {
+            if (s + Op::spec(A).lead >= za - Op::spec(A).zlo)
+                fallback_fill<Op, A>(P, stage, X0, Y0, s + Op::spec(A).lead, lane);
+            ProducerIssue<Op, A + 1>::fallback(P, stage, X0, Y0, s, za, lane);
+        }
+    }
+};
+
+struct ItemCoords { int X0, Y0, za, zb; };
+
+template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int item)
+{
+    const int tiles_xy = P.ntx * P.nty;
+    const int zc = item / tiles_xy;
+    const int t = item - zc * tiles_xy;
+    const int tyi = t / P.ntx, txi = t - tyi * P.ntx;
+    ItemCoords c;
+    c.X0 = txi * Op::TX;                       // x tiles start at 0 so vectors stay 16-byte aligned
+    c.Y0 = P.ylo + tyi * Op::TY;
+    c.za = P.z0 + zc * P.zc_len;
+    c.zb = min(P.z1, c.za + P.zc_len);
+    return c;
+}
+
+template <class Op>
+__global__ void __launch_bounds__(NTHREADS, Op::MIN_BLOCKS)
+stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ TensorMaps M)
+{
+    using G = Geo<Op>;
+    constexpr int S = Op::STAGES;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + S;
+    unsigned char* stages = smem + 128;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < S; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], NCONS / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NCONS / 32) {
+        // ------------------------------ producer warp ------------------------------
+        if (P.use_tma) {
+            if (lane != 0) return;
+#pragma unroll
+            for (int a = 0; a < Op::NSTAGED; a++) tma_prefetch_desc(&M.m[a]);
+        }
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+            const ItemCoords c = decode_item<Op>(P, item);
+            for (int s = c.za - Op::WARM; s < c.zb; ++s, ++g) {
+                const uint32_t st = g % S, ph = (g / S) & 1u;
+                mbar_wait(&empty[st], ph ^ 1u);
+                unsigned char* sb = stages + st * G::STAGE_BYTES;
+                if (P.use_tma) {
+                    uint32_t bytes = 0;
+                    ProducerIssue<Op, 0>::bytes(s, c.za, bytes);
+                    mbar_arrive_expect_tx(&full[st], bytes);
+                    ProducerIssue<Op, 0>::tma(M, sb, &full[st], c.X0, c.Y0, s, c.za);
+                } else {
+                    ProducerIssue<Op, 0>::fallback(P, sb, c.X0, c.Y0, s, c.za, lane);
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[st]);
+                }
+            }
+        }
+    } else {
+        // ------------------------------ consumer warps ------------------------------
+        Op op(P);
+        typename Op::State state;
+        Ctx<Op> ctx{P, stages, 0u, 0, 0, 0, 0, tid % G::LX, tid / G::LX};
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+            const ItemCoords c = decode_item<Op>(P, item);
+            ctx.X0 = c.X0;
+            ctx.Y0 = c.Y0;
+            int local = 0;
+            for (int s = c.za - Op::WARM; s < c.zb; ++s, ++g, ++local) {
+                const uint32_t st = g % S, ph = (g / S) & 1u;
+                ctx.g = g;
+                ctx.s = s;
+                ctx.rel = s - c.za;
+                op.pre(ctx, state);
+                mbar_wait(&full[st], ph);
+                op.step(ctx, state);
+                if (local >= Op::HOLD) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[(g - (uint32_t)Op::HOLD) % S]);
+                }
+            }
+            if constexpr (Op::HOLD > 0) {
+                // hand back the stages still held at the end of the item
+                const int held = local < Op::HOLD ? local : Op::HOLD;
+                __syncwarp();
+                if (lane == 0)
+                    for (int h = held; h >= 1; h--) mbar_arrive(&empty[(g - (uint32_t)h) % S]);
+            }
+        }
+    }
+}
+
+}  // namespace b200

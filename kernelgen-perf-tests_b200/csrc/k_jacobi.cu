@@ -1,0 +1,7 @@
+// k_jacobi.cu -- instantiates the jacobi stencil (float + double) of the tile-streaming engine.
+#include "b200_launch.cuh"
+#include "b200_ops2d.cuh"
+
+namespace b200 {
+B200_DEFINE_OP(jacobi, JacobiOp)
+}  // namespace b200

@@ -1,0 +1,137 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI exactly as the C drivers
+call it (b200_init / plan / alloc / load / run / save on HOST buffers), against
+  * the committed golden fixtures (outputs of the reference itself, tests/golden/), and
+  * the CPU oracle on the same rand()-initialised inputs, at ragged / odd / TMA-incompatible
+    sizes and at the README size 512x256x256.
+Bars: gameoflife bit-exact vs the strict-IEEE build; every other test normwise
+max|gpu-ref|/max|ref| <= 1e-12 (double) / 1e-5 (float) (FMA contraction + re-association);
+uxx1 with the condition-aware per-point bound of parity_util.uxx1_bound.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from parity_util import TOL, normwise, uxx1_bound
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
+STENCILS = ["laplacian", "wave13pt", "divergence", "gradient", "uxx1", "lapgsrb", "jacobi",
+            "gaussblur", "gameoflife", "tricubic", "tricubic2", "vecadd", "matvec", "sincos"]
+FIXTURE_TESTS = [t for t in STENCILS if t not in ("jacobi", "sincos")]
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    c = pkg.Context(1)
+    yield c
+    c.destroy()
+
+
+def gpu_run(ctx, test, real, nx, ny, ns, nt, scalars, arrays):
+    work = [a.copy() for a in arrays]
+    slot, stats = ctx.run_on_host_arrays(test, real, nx, ny, ns, scalars, work, nt)
+    return slot, work, stats
+
+
+def check(test, real, nx, ny, ns, nt, scalars, inputs, got, want, strict_want=None):
+    if test == "gameoflife":
+        ref = strict_want if strict_want is not None else want
+        for q in range(len(got)):
+            assert np.array_equal(got[q], ref[q]), f"gameoflife/{real}: slot {q} not bit-exact vs strict oracle"
+        return
+    if test == "uxx1":
+        bound = uxx1_bound(scalars, inputs, nx, ny, ns, real, nt)
+        for q in (0, 1):
+            err = np.abs(got[q].astype(np.float64) - want[q].astype(np.float64))
+            bad = err > bound + 1e-300
+            assert not bad.any(), (f"uxx1/{real}: slot {q}: {int(bad.sum())} points beyond the condition-aware bound; "
+                                   f"worst ratio {float(np.max(err[bad] / np.maximum(bound[bad], 1e-300))):.3g}")
+        for q in range(2, 6):
+            assert np.array_equal(got[q], want[q])
+        return
+    for q in range(len(got)):
+        e = normwise(got[q], want[q])
+        assert e <= TOL[real], f"{test}/{real} {nx}x{ny}x{ns} nt={nt}: slot {q} normwise error {e:.3e}"
+
+
+@pytest.mark.parametrize("real", ["float", "double"])
+@pytest.mark.parametrize("test", FIXTURE_TESTS)
+def test_golden_fixtures(ctx, test, real):
+    """Against outputs of the reference itself (shipped flags and strict build)."""
+    fx = np.load(GOLDEN_DIR / f"{test}_{real}.npz")
+    nx, ny, ns, nt = [int(v) for v in fx["dims"]]
+    scalars = [float(v) for v in fx["scalars"]]
+    n = len([k for k in fx.files if k.startswith("in")])
+    inputs = [fx[f"in{q}"] for q in range(n)]
+    slot, got, stats = gpu_run(ctx, test, real, nx, ny, ns, nt, scalars, inputs)
+    shipped = [fx[f"shipped{q}"] if f"shipped{q}" in fx.files else fx[f"in{q}"] for q in range(n)]
+    strict = [fx[f"strict{q}"] if f"strict{q}" in fx.files else fx[f"in{q}"] for q in range(n)]
+    check(test, real, nx, ny, ns, nt, scalars, inputs, got, shipped, strict)
+    if test != "gameoflife":
+        check(test, real, nx, ny, ns, nt, scalars, inputs, got, strict)
+    else:
+        # vs the shipped (fast-math) build only a pointwise-relative bound is meaningful
+        rtol = 1e-8 if real == "double" else 1e-2
+        assert np.allclose(got[0], shipped[0], rtol=rtol, atol=0) and np.allclose(got[1], shipped[1], rtol=rtol, atol=0)
+    assert stats["launches"] == nt
+
+
+SIZES_3D = [(128, 20, 12), (130, 37, 29), (63, 31, 29), (260, 19, 11), (16, 5, 5), (5, 5, 5)]
+SIZES_2D = [(128, 70, 1), (130, 517, 1), (63, 301, 1), (512, 300, 1), (5, 5, 1)]
+
+
+@pytest.mark.parametrize("real", ["float", "double"])
+@pytest.mark.parametrize("test", STENCILS)
+def test_vs_oracle_ragged_sizes(ctx, oracle, oracle_strict, test, real):
+    """Same rand() inputs, odd / ragged / tiny extents (TMA path and scalar-loader path), 3 sweeps
+    with the driver's buffer rotation, every array compared (untouched shells included)."""
+    info = oracle.info(test)
+    for nx, ny, ns in (SIZES_3D if info["ndims"] == 3 else SIZES_2D):
+        for nt in (1, 3):
+            scalars, inputs, _ = oracle.init(test, real, nx, ny, ns)
+            o = oracle_strict if test == "gameoflife" else oracle
+            want = [a.copy() for a in inputs]
+            slot_o = o.run(test, real, nx, ny, ns, nt, scalars, want)
+            slot, got, stats = gpu_run(ctx, test, real, nx, ny, ns, nt, scalars, inputs)
+            assert slot == slot_o, f"{test}: result slot {slot} != reference remap {slot_o}"
+            check(test, real, nx, ny, ns, nt, scalars, inputs, got, want)
+
+
+@pytest.mark.parametrize("test", ["laplacian", "wave13pt", "lapgsrb", "uxx1", "divergence", "gradient",
+                                  "gameoflife", "gaussblur", "jacobi", "vecadd", "matvec"])
+def test_readme_size_double(ctx, pkg, test):
+    """512 256 256 (2D: 512 x 65536), double, 2 sweeps, element-wise vs the threaded oracle, and the
+    driver-level checksums: i_mean / f_mean the way the reference prints them."""
+    from oracle_util import Oracle
+    o = Oracle("omp")
+    os_ = Oracle("strict")
+    info = o.info(test)
+    nx, ny, ns = (512, 256, 256) if info["ndims"] == 3 else (512, 65536, 1)
+    nt = 2
+    scalars, inputs, _ = o.init(test, "double", nx, ny, ns)
+    want = [a.copy() for a in inputs]
+    (os_ if test == "gameoflife" else o).run(test, "double", nx, ny, ns, nt, scalars, want)
+    slot, got, stats = gpu_run(ctx, test, "double", nx, ny, ns, nt, scalars, inputs)
+    check(test, "double", nx, ny, ns, nt, scalars, inputs, got, want)
+    fm_gpu = o.final_mean(test, "double", nx, ny, ns, got, slot)
+    fm_ref = o.final_mean(test, "double", nx, ny, ns, want, slot)
+    assert "%f" % fm_gpu == "%f" % fm_ref
+
+
+def test_degenerate_and_errors(ctx, pkg):
+    a = [np.ones(27), np.ones(27) * 2]
+    slot, got, _ = gpu_run(ctx, "wave13pt", "double", 3, 3, 3, 2, [0.1, 0.2, 0.3], a + [np.ones(27) * 3])
+    assert np.array_equal(got[0], a[0])            # interior empty: nothing written
+    with pytest.raises(pkg.B200Error):
+        ctx.plan("laplacian", "double", 8, 8, 8, [0.1])       # wrong scalar count
+    with pytest.raises(pkg.B200Error):
+        ctx.plan("laplacian", "double", -1, 8, 8, [0.1, 0.2])
+
+
+def test_kernel_info(pkg):
+    for t in STENCILS:
+        for real in ("float", "double"):
+            ki = pkg.kernel_info(t, real)
+            assert 16 <= ki["regs"] <= 255 and ki["name"] == t
