@@ -152,6 +152,23 @@ int b200_destroy(b200_ctx* ctx);
 int b200_host_alloc(void** ptr, size_t bytes);
 int b200_host_free(void* ptr);
 
+/* ---- one-process-per-GPU slabs: peer memory + device-side ordering -------------------------
+ * For launchers that run one process per GPU (torchrun): device buffers that can be exported
+ * to the neighbour ranks over CUDA IPC, so that b200_sweep's push_lo / push_hi pointers reach
+ * the neighbour's ghost planes over NVLink, and a flag per neighbour for ordering: after its
+ * sweep a rank signals the neighbours (b200_signal stores `value` to a flag in THEIR memory,
+ * release at system scope); before the next sweep it waits (b200_wait spins on its own flag on
+ * the device, acquire at system scope) -- no host round trip, no collective on the data path.
+ * b200_wait traps after ~20 s instead of hanging. */
+#define B200_IPC_HANDLE_BYTES 64
+int b200_device_alloc(void** ptr, size_t bytes);
+int b200_device_free(void* ptr);
+int b200_ipc_export(void* dev_ptr, void* handle /* B200_IPC_HANDLE_BYTES */);
+int b200_ipc_import(const void* handle, void** peer_ptr);
+int b200_ipc_close(void* peer_ptr);
+int b200_signal(void* flag, unsigned long long value, void* stream);
+int b200_wait(const void* flag, unsigned long long value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

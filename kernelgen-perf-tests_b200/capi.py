@@ -29,7 +29,9 @@ EXPORTS = ["b200_get_test_info", "b200_test_by_name", "b200_last_error", "b200_a
            "b200_interior_points", "b200_device_count", "b200_sweep", "b200_kernel_info",
            "b200_launch_count", "b200_init", "b200_plan", "b200_alloc", "b200_load", "b200_run",
            "b200_result_slot", "b200_save", "b200_free", "b200_destroy", "b200_host_alloc",
-           "b200_host_free"]
+           "b200_host_free", "b200_device_alloc", "b200_device_free", "b200_ipc_export",
+           "b200_ipc_import", "b200_ipc_close", "b200_signal", "b200_wait"]
+IPC_HANDLE_BYTES = 64
 
 
 class B200Error(RuntimeError):
@@ -93,6 +95,13 @@ def load() -> C.CDLL:
     L.b200_destroy.argtypes = [C.c_void_p]
     L.b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.b200_host_free.argtypes = [C.c_void_p]
+    L.b200_device_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.b200_device_free.argtypes = [C.c_void_p]
+    L.b200_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+    L.b200_ipc_import.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.b200_ipc_close.argtypes = [C.c_void_p]
+    L.b200_signal.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p]
+    L.b200_wait.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p]
     _lib = L
     return L
 
@@ -150,6 +159,40 @@ def sweep(test, dtype, nx, ny, ns, scalars, device_ptrs, stream=0, out_range=Non
             d.push_hi, d.push_hi_src_plane, d.push_hi_dst_plane, d.push_hi_count = push["hi"]
     ptrs = (C.c_void_p * len(device_ptrs))(*device_ptrs)
     _check(load().b200_sweep(C.byref(d), ptrs, C.c_void_p(stream)))
+
+
+def device_alloc(nbytes: int) -> int:
+    p = C.c_void_p()
+    _check(load().b200_device_alloc(C.byref(p), nbytes))
+    return p.value
+
+
+def device_free(ptr: int):
+    _check(load().b200_device_free(C.c_void_p(ptr)))
+
+
+def ipc_export(ptr: int) -> bytes:
+    buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+    _check(load().b200_ipc_export(C.c_void_p(ptr), buf))
+    return buf.raw
+
+
+def ipc_import(handle: bytes) -> int:
+    p = C.c_void_p()
+    _check(load().b200_ipc_import(handle, C.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr: int):
+    _check(load().b200_ipc_close(C.c_void_p(ptr)))
+
+
+def signal_flag(flag_ptr: int, value: int, stream: int = 0):
+    _check(load().b200_signal(C.c_void_p(flag_ptr), value, C.c_void_p(stream)))
+
+
+def wait_flag(flag_ptr: int, value: int, stream: int = 0):
+    _check(load().b200_wait(C.c_void_p(flag_ptr), value, C.c_void_p(stream)))
 
 
 class PinnedBuffer:

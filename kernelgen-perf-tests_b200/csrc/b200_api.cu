@@ -261,6 +261,84 @@ int b200_host_free(void* ptr)
 }
 
 // ------------------------------------------------------------------------------------------
+// one-process-per-GPU helpers: IPC-exportable buffers, device-side signal / wait
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+__global__ void b200_signal_kernel(unsigned long long* flag, unsigned long long value)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+
+__global__ void b200_wait_kernel(const unsigned long long* flag, unsigned long long value, unsigned long long timeout_ns)
+{
+    unsigned long long t0, now, cur;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
+        if (cur >= value) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) __trap();       // a neighbour died: fail instead of hanging the box
+        __nanosleep(200);
+    }
+}
+
+extern "C" {
+
+int b200_device_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) { set_error("NULL argument"); return B200_ERR_ARG; }
+    B200_CUDA(cudaMalloc(ptr, bytes ? bytes : 16));
+    return B200_OK;
+}
+
+int b200_device_free(void* ptr)
+{
+    if (ptr) B200_CUDA(cudaFree(ptr));
+    return B200_OK;
+}
+
+int b200_ipc_export(void* dev_ptr, void* handle)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!dev_ptr || !handle) { set_error("NULL argument"); return B200_ERR_ARG; }
+    B200_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle, dev_ptr));
+    return B200_OK;
+}
+
+int b200_ipc_import(const void* handle, void** peer_ptr)
+{
+    if (!handle || !peer_ptr) { set_error("NULL argument"); return B200_ERR_ARG; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    B200_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200_OK;
+}
+
+int b200_ipc_close(void* peer_ptr)
+{
+    if (peer_ptr) B200_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return B200_OK;
+}
+
+int b200_signal(void* flag, unsigned long long value, void* stream)
+{
+    if (!flag) { set_error("NULL argument"); return B200_ERR_ARG; }
+    b200_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)flag, value);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+int b200_wait(const void* flag, unsigned long long value, void* stream)
+{
+    if (!flag) { set_error("NULL argument"); return B200_ERR_ARG; }
+    b200_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned long long*)flag, value, 20000000000ull);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // context API
 // ------------------------------------------------------------------------------------------
 struct b200_slab {

@@ -1,0 +1,372 @@
+"""z-slab engine: one process per GPU, the grid cut into contiguous slabs along the slowest
+dimension (z for the 3D tests, y for the 2D tests), ghost planes refreshed once per sweep.
+
+Host-side logic only -- the sweeps are launched through the C ABI (capi.sweep).  Two ways to
+refresh ghosts:
+
+  halo="push"  the sweep kernel stores the planes a neighbour needs straight into the
+               neighbour's memory (CUDA-IPC peer pointer, NVLink); ordering between ranks is a
+               device-side flag per neighbour (b200_signal / b200_wait), no host round trip and
+               no collective on the data path;
+  halo="nccl"  torch.distributed batched isend/irecv of the boundary planes after each sweep
+               (also what the CPU/gloo tests use).
+
+torch provides device memory, streams, events and torch.distributed; nothing else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+class SlabLayout:
+    """Pure arithmetic: which planes a rank owns / stores / exchanges."""
+
+    def __init__(self, info: dict, n_global: int, world: int, rank: int):
+        self.info, self.n, self.world, self.rank = info, n_global, world, rank
+        self.split_dim = 2 if info["ndims"] == 3 else 1
+        glo, ghi = info["zghost_lo"], info["zghost_hi"]
+        self.own_lo = n_global * rank // world
+        self.own_hi = n_global * (rank + 1) // world
+        self.mem_lo = max(0, self.own_lo - glo)
+        self.mem_hi = min(n_global, self.own_hi + ghi)
+        if world > 1 and self.own_hi - self.own_lo < glo + ghi + 1:
+            raise ValueError(f"extent {n_global} too small for {world} slabs")
+        self.lo_ghost = self.own_lo - self.mem_lo        # planes received from rank-1
+        self.hi_ghost = self.mem_hi - self.own_hi        # planes received from rank+1
+        # what the neighbours need from us
+        self.send_lo_cnt = ghi if rank > 0 else 0          # our lowest owned planes -> rank-1's upper ghosts
+        self.send_hi_cnt = glo if rank < world - 1 else 0  # our highest owned planes -> rank+1's lower ghosts
+
+    @property
+    def mem_n(self):
+        return self.mem_hi - self.mem_lo
+
+    def out_range(self):
+        """Owned planes inside the global interior, in LOCAL coordinates (half-open)."""
+        lo = max(self.own_lo, self.info["lo"][self.split_dim])
+        hi = min(self.own_hi, self.n - self.info["hi"][self.split_dim])
+        return lo - self.mem_lo, max(hi, lo) - self.mem_lo
+
+    # local plane ranges
+    def send_lo(self):
+        a = self.own_lo - self.mem_lo
+        return a, a + self.send_lo_cnt
+
+    def send_hi(self):
+        b = self.own_hi - self.mem_lo
+        return b - self.send_hi_cnt, b
+
+    def recv_lo(self):
+        return 0, self.lo_ghost
+
+    def recv_hi(self):
+        b = self.own_hi - self.mem_lo
+        return b, b + self.hi_ghost
+
+
+def exchange_halos(dist, layout: SlabLayout, t):
+    """Refresh the ghost planes of tensor `t` (leading dimension = split dimension) with the
+    neighbours' boundary planes: torch.distributed point-to-point, any backend."""
+    ops = []
+    r = layout.rank
+    if layout.send_lo_cnt:
+        a, b = layout.send_lo()
+        ops.append(dist.P2POp(dist.isend, t[a:b], r - 1))
+    if layout.send_hi_cnt:
+        a, b = layout.send_hi()
+        ops.append(dist.P2POp(dist.isend, t[a:b], r + 1))
+    if layout.lo_ghost:
+        a, b = layout.recv_lo()
+        ops.append(dist.P2POp(dist.irecv, t[a:b], r - 1))
+    if layout.hi_ghost:
+        a, b = layout.recv_hi()
+        ops.append(dist.P2POp(dist.irecv, t[a:b], r + 1))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+class _DevMem:
+    """cudaMalloc'ed memory from the C ABI (IPC-exportable), viewable as a torch tensor."""
+
+    def __init__(self, pkg, nelem, np_dtype):
+        self.pkg, self.nelem, self.dtype = pkg, nelem, np.dtype(np_dtype)
+        self.ptr = pkg.capi.device_alloc(nelem * self.dtype.itemsize)
+        self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": self.dtype.str, "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+
+    def tensor(self, torch):
+        return torch.as_tensor(self, device="cuda")
+
+    def free(self):
+        if self.ptr:
+            self.pkg.capi.device_free(self.ptr)
+            self.ptr = 0
+
+
+class SlabEngine:
+    """One rank's slab of one test: buffers, rotation, sweeps, ghost refresh."""
+
+    def __init__(self, pkg, test, real, nx, ny, ns, scalars, world=1, rank=0, dist=None, halo="push", seed=0):
+        import torch
+        self.torch, self.pkg, self.dist = torch, pkg, dist
+        self.test, self.real, self.scalars = test, real, list(scalars)
+        self.info = info = pkg.test_info(test)
+        self.world, self.rank, self.halo = world, rank, halo
+        self.nx, self.ny, self.ns = nx, ny, (ns if info["ndims"] == 3 else 1)
+        self.np_dtype = np.float32 if real == "float" else np.float64
+        per_rank = self.ns if info["ndims"] == 3 else ny
+        self.layout = L = SlabLayout(info, per_rank * world, world, rank)
+        self.exchange = world > 1 and info["exchange_slot"] >= 0
+        self.unit = nx * ny if info["ndims"] == 3 else nx            # elements per plane / row
+        if test == "matvec":
+            self.unit = nx
+        self.stream = torch.cuda.current_stream()
+        # buffers: slab incl. ghosts, from the C ABI allocator (IPC-exportable)
+        self.mem, self.t = [], []
+        g = torch.Generator(device="cuda")
+        g.manual_seed(seed)
+        for q in range(info["narrays"]):
+            n = self._slot_len(q)
+            m = _DevMem(pkg, n, self.np_dtype)
+            t = m.tensor(torch)
+            t.copy_(torch.rand(n, generator=g, device="cuda", dtype=t.dtype) * 2 - 1)
+            self.mem.append(m)
+            self.t.append(t)
+        self.idxs = [0, 1, 2]
+        self.sweeps_done = 0
+        self.peer = {}
+        if self.exchange:
+            # consistent ghosts to start from (all rotating buffers)
+            for q in range(info["rotation"]):
+                exchange_halos(dist, L, self.t[q].view(L.mem_n, -1))
+            if halo == "push":
+                self._setup_push()
+        torch.cuda.synchronize()
+
+    # -- sizes -------------------------------------------------------------------------------
+    def _slot_len(self, q):
+        if self.test == "matvec":
+            return [self.nx * self.layout.mem_n, self.nx, self.layout.mem_n][q]
+        return self.unit * self.layout.mem_n
+
+    def local_dims(self):
+        L = self.layout
+        if self.info["ndims"] == 3:
+            return self.nx, self.ny, L.mem_n
+        return self.nx, L.mem_n, 1
+
+    def local_interior_points(self):
+        a, b = self.layout.out_range()
+        i = self.info
+        if self.test == "matvec":
+            return self.nx * (b - a)
+        ex = self.nx - i["lo"][0] - i["hi"][0]
+        ey = (self.ny - i["lo"][1] - i["hi"][1]) if i["ndims"] == 3 else 1
+        return max(ex, 0) * max(ey, 0) * max(b - a, 0)
+
+    def global_interior_points(self):
+        L = self.layout
+        if self.info["ndims"] == 3:
+            return self.pkg.interior_points(self.test, self.nx, self.ny, L.n)
+        return self.pkg.interior_points(self.test, self.nx, L.n, 1)
+
+    # -- push mode plumbing --------------------------------------------------------------------
+    def _setup_push(self):
+        torch, dist, capi = self.torch, self.dist, self.pkg.capi
+        nrot = self.info["rotation"]
+        self.flags = _DevMem(self.pkg, 8, np.int64)             # [0]: written by rank-1, [1]: by rank+1
+        self.flags.tensor(torch).zero_()
+        torch.cuda.synchronize()
+        mine = {"bufs": [capi.ipc_export(self.mem[q].ptr) for q in range(nrot)],
+                "flags": capi.ipc_export(self.flags.ptr)}
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine)
+        for nb in (self.rank - 1, self.rank + 1):
+            if 0 <= nb < self.world:
+                self.peer[nb] = {"bufs": [capi.ipc_import(h) for h in allh[nb]["bufs"]],
+                                 "flags": capi.ipc_import(allh[nb]["flags"])}
+        dist.barrier()
+
+    def _push_desc(self, out_slot):
+        """Peer pointers + plane ranges for the fused halo push of this sweep's output array."""
+        L, push = self.layout, {}
+        esz = np.dtype(self.np_dtype).itemsize
+        peers = getattr(self, "_peer_layouts", None)
+        if peers is None:
+            peers = self._peer_layouts = {nb: SlabLayout(self.info, L.n, self.world, nb) for nb in self.peer}
+        if self.rank - 1 in self.peer:
+            n = peers[self.rank - 1]
+            a, _ = L.send_lo()
+            push["lo"] = (self.peer[self.rank - 1]["bufs"][out_slot], a, n.own_hi - n.mem_lo, L.send_lo_cnt)
+        if self.rank + 1 in self.peer:
+            a, _ = L.send_hi()
+            push["hi"] = (self.peer[self.rank + 1]["bufs"][out_slot], a, 0, L.send_hi_cnt)
+        return push
+
+    # -- the hot loop --------------------------------------------------------------------------
+    def run(self, niters: int):
+        """`niters` sweeps with the reference driver's buffer rotation (laplacian.c:287-301)."""
+        capi, info, L = self.pkg.capi, self.info, self.layout
+        nx, ny, ns = self.local_dims()
+        rot = info["rotation"]
+        out_pos = 2 if rot == 3 else 1
+        stream = self.stream.cuda_stream
+        a, b = L.out_range()
+        out_range = (a, b) if (self.world > 1 or self.test in ("vecadd", "sincos", "matvec")) else None
+        for _ in range(niters):
+            ptrs = [m.ptr for m in self.mem]
+            for q in range(rot):
+                ptrs[q] = self.mem[self.idxs[q]].ptr
+            push = None
+            if self.exchange and self.halo == "push":
+                it = self.sweeps_done
+                if it > 0:
+                    # ghosts of this sweep's input were pushed during the neighbours' previous sweep
+                    if self.rank - 1 in self.peer:
+                        capi.wait_flag(self.flags.ptr, it, stream)
+                    if self.rank + 1 in self.peer:
+                        capi.wait_flag(self.flags.ptr + 8, it, stream)
+                push = self._push_desc(self.idxs[out_pos])
+            if b > a:
+                capi.sweep(self.test, self.real, nx, ny, ns, self.scalars, ptrs, stream=stream,
+                           out_range=out_range, push=push)
+            if self.exchange:
+                if self.halo == "push":
+                    it = self.sweeps_done + 1
+                    if self.rank - 1 in self.peer:      # we are rank-1's upper neighbour -> its flag[1]
+                        capi.signal_flag(self.peer[self.rank - 1]["flags"] + 8, it, stream)
+                    if self.rank + 1 in self.peer:      # we are rank+1's lower neighbour -> its flag[0]
+                        capi.signal_flag(self.peer[self.rank + 1]["flags"], it, stream)
+                else:
+                    exchange_halos(self.dist, L, self.t[self.idxs[out_pos]].view(L.mem_n, -1))
+            if rot == 2:
+                self.idxs[0], self.idxs[1] = self.idxs[1], self.idxs[0]
+            elif rot == 3:
+                self.idxs = [self.idxs[1], self.idxs[2], self.idxs[0]]
+            self.sweeps_done += 1
+
+    def result_slot(self):
+        if self.info["rotation"]:
+            return self.idxs[1]
+        return {"divergence": 0, "gradient": 1}.get(self.test, 2)
+
+    # -- end to end on host buffers ---------------------------------------------------------------
+    def e2e(self, niters, steps, barrier, dist=None):
+        """Per step: H2D of every array from pinned host memory, niters sweeps, D2H of the result.
+        N=1 goes through the driver-phase C ABI (b200_load / b200_run / b200_save); N>1 copies each
+        rank's slab with cudaMemcpyAsync on the sweep stream."""
+        import time
+        torch, capi = self.torch, self.pkg.capi
+        esz = np.dtype(self.np_dtype).itemsize
+        nbytes_in = sum(self._slot_len(q) for q in range(self.info["narrays"])) * esz
+        if self.world == 1:
+            nx, ny, ns = self.local_dims()
+            host = [capi.PinnedBuffer(self._slot_len(q), self.np_dtype) for q in range(self.info["narrays"])]
+            rng = np.random.default_rng(7)
+            for h in host:
+                h.array[:] = rng.uniform(-1, 1, h.array.size).astype(self.np_dtype)
+            ctx = capi.Context(1)
+            ctx.plan(self.test, self.real, nx, ny, ns if self.info["ndims"] == 3 else 1, self.scalars)
+            ctx.alloc()
+
+            def step():
+                for q, h in enumerate(host):
+                    ctx.load_array(q, h.array)
+                ctx.run(niters)
+                slot = ctx.result_slot()
+                ctx.save_array(slot, host[slot].array)
+                return slot
+
+            step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                slot = step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / steps
+            nbytes_out = host[slot].array.nbytes
+            ctx.free()
+            ctx.destroy()
+            for h in host:
+                h.free()
+            return {"seconds_per_step": dt, "h2d_bytes_per_step": int(nbytes_in), "d2h_bytes_per_step": int(nbytes_out),
+                    "api": "b200_load/b200_run/b200_save (C ABI, pinned host buffers)", "steps": steps}
+        host = [torch.empty(self._slot_len(q), dtype=self.t[q].dtype).pin_memory() for q in range(self.info["narrays"])]
+        for h in host:
+            h.uniform_(-1, 1)
+
+        def step():
+            for q, h in enumerate(host):
+                self.t[q].copy_(h, non_blocking=True)
+            self.run(niters)
+            slot = self.result_slot()
+            host[slot].copy_(self.t[slot], non_blocking=True)
+            return slot
+
+        step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            slot = step()
+        barrier()
+        dt = (time.perf_counter() - t0) / steps
+        if dist is not None:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        return {"seconds_per_step": dt, "h2d_bytes_per_step": int(nbytes_in) * self.world,
+                "d2h_bytes_per_step": int(host[slot].numel() * esz) * self.world,
+                "api": "per-rank pinned slab copies + b200_sweep (C ABI)", "steps": steps}
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        capi = self.pkg.capi
+        for nb, p in self.peer.items():
+            for ptr in p["bufs"]:
+                capi.ipc_close(ptr)
+            capi.ipc_close(p["flags"])
+        self.peer = {}
+        if self.dist is not None:
+            self.dist.barrier()
+        self.t = []
+        for m in self.mem:
+            m.free()
+        if hasattr(self, "flags"):
+            self.flags.free()
+
+
+def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3):
+    """GLUP/s and fraction of the HBM roofline for every test, float and double, on cuda:0."""
+    import torch
+    rows = []
+    sizes = [("C1", (512, 256, 256))] + ([("C2", (1024, 1024, 512))] if full else [])
+    for label, (nx, ny, ns) in sizes:
+        for test in pkg.TESTS:
+            info = pkg.test_info(test)
+            for real in ("double", "float"):
+                dims = (nx, ny, ns) if info["ndims"] == 3 else (nx, ny * ns, 1)
+                try:
+                    eng = SlabEngine(pkg, test, real, dims[0], dims[1], dims[2], scalars.get(test, []))
+                    eng.run(niters)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(reps):
+                        eng.run(niters)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    sec = e0.elapsed_time(e1) * 1e-3 / (reps * niters)
+                    lups = eng.local_interior_points()
+                    bpl = (info["nread"] + info["nwritten"]) * (4 if real == "float" else 8)
+                    rows.append({"test": test, "real": real, "size": f"{dims[0]}x{dims[1]}x{dims[2]}", "cfg": label,
+                                 "us_per_sweep": round(sec * 1e6, 2), "glups": round(lups / sec / 1e9, 2),
+                                 "gbs": round(lups * bpl / sec / 1e9, 1), "frac": round(lups * bpl / sec / 1e9 / peak_gbs, 4),
+                                 "regs": pkg.kernel_info(test, real)["regs"]})
+                    eng.close()
+                except Exception as e:      # keep the headline alive; report the failure
+                    rows.append({"test": test, "real": real, "cfg": label, "error": str(e)[:200]})
+                    torch.cuda.synchronize()
+    return rows
