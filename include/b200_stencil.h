@@ -113,11 +113,21 @@ typedef struct {
      * receives our planes [push_lo_src_plane, +zghost_hi); likewise for hi. */
     void* push_lo; int push_lo_src_plane; int push_lo_dst_plane; int push_lo_count;
     void* push_hi; int push_hi_src_plane; int push_hi_dst_plane; int push_hi_count;
+    /* 1: walk the work items back to front.  Alternating 0/1 between consecutive sweeps makes a
+     * sweep start on the data its predecessor touched last, which is still in L2. */
+    int reverse_order;
 } b200_sweep_desc;
 
 /* One sweep: arrays[] are DEVICE pointers in slot order (current rotation
  * already applied by the caller).  Asynchronous on `stream`. */
 int b200_sweep(const b200_sweep_desc* desc, void* const* arrays, void* stream);
+
+/* `niters` sweeps enqueued back to back with the reference driver's buffer rotation applied
+ * between them (the nt-loop of laplacian/laplacian.c:287-301 without its per-iteration
+ * cudaDeviceSynchronize).  arrays[] is rotated IN PLACE: on return it holds the pointers in
+ * the order the next sweep would see them.  Not for sweeps that push halos (those need the
+ * per-sweep b200_wait / b200_signal ordering). */
+int b200_sweep_loop(const b200_sweep_desc* desc, void** arrays, int niters, void* stream);
 
 /* Registers per thread / kernel symbol of the kernel b200_sweep would launch. */
 int b200_kernel_info(int test, int dtype, int* regs_per_thread, const char** kernel_name);

@@ -26,7 +26,7 @@ MAX_ARRAYS, MAX_SCALARS = 8, 8
 
 # every symbol include/b200_stencil.h declares (checked by tests/test_abi.py)
 EXPORTS = ["b200_get_test_info", "b200_test_by_name", "b200_last_error", "b200_api_version",
-           "b200_interior_points", "b200_device_count", "b200_sweep", "b200_kernel_info",
+           "b200_interior_points", "b200_device_count", "b200_sweep", "b200_sweep_loop", "b200_kernel_info",
            "b200_launch_count", "b200_init", "b200_plan", "b200_alloc", "b200_load", "b200_run",
            "b200_result_slot", "b200_save", "b200_free", "b200_destroy", "b200_host_alloc",
            "b200_host_free", "b200_device_alloc", "b200_device_free", "b200_ipc_export",
@@ -51,7 +51,7 @@ class SweepDesc(C.Structure):
                 ("push_lo", C.c_void_p), ("push_lo_src_plane", C.c_int), ("push_lo_dst_plane", C.c_int),
                 ("push_lo_count", C.c_int),
                 ("push_hi", C.c_void_p), ("push_hi_src_plane", C.c_int), ("push_hi_dst_plane", C.c_int),
-                ("push_hi_count", C.c_int)]
+                ("push_hi_count", C.c_int), ("reverse_order", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     L.b200_interior_points.argtypes = [C.c_int] * 4
     L.b200_device_count.argtypes = [C.POINTER(C.c_int)]
     L.b200_sweep.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.c_void_p]
+    L.b200_sweep_loop.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
     L.b200_kernel_info.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_char_p)]
     L.b200_launch_count.restype = C.c_ulonglong
     L.b200_init.argtypes = [C.POINTER(C.c_void_p), C.c_int]
@@ -159,6 +160,20 @@ def sweep(test, dtype, nx, ny, ns, scalars, device_ptrs, stream=0, out_range=Non
             d.push_hi, d.push_hi_src_plane, d.push_hi_dst_plane, d.push_hi_count = push["hi"]
     ptrs = (C.c_void_p * len(device_ptrs))(*device_ptrs)
     _check(load().b200_sweep(C.byref(d), ptrs, C.c_void_p(stream)))
+
+
+def sweep_loop(test, dtype, nx, ny, ns, scalars, device_ptrs, niters, stream=0, out_range=None):
+    """`niters` sweeps back to back with the reference rotation applied in C; returns the rotated
+    pointer list (the order the next sweep would see)."""
+    d = SweepDesc()
+    d.test, d.dtype, d.nx, d.ny, d.ns = _tid(test), _DT[dtype], nx, ny, ns
+    for i, v in enumerate(scalars):
+        d.scalars[i] = float(v)
+    if out_range is not None:
+        d.out_begin, d.out_end = out_range
+    ptrs = (C.c_void_p * len(device_ptrs))(*device_ptrs)
+    _check(load().b200_sweep_loop(C.byref(d), ptrs, niters, C.c_void_p(stream)))
+    return [int(p) if p else 0 for p in ptrs]
 
 
 def device_alloc(nbytes: int) -> int:

@@ -233,6 +233,28 @@ int b200_sweep(const b200_sweep_desc* desc, void* const* arrays, void* stream)
     return g_launch[desc->test](desc->dtype, a);
 }
 
+int b200_sweep_loop(const b200_sweep_desc* desc, void** arrays, int niters, void* stream)
+{
+    if (int rc = check_sweep_args(desc, arrays)) return rc;
+    if (niters < 0) { set_error("negative iteration count"); return B200_ERR_ARG; }
+    if (desc->push_lo || desc->push_hi) { set_error("b200_sweep_loop: halo push needs per-sweep ordering, use b200_sweep"); return B200_ERR_ARG; }
+    const b200_test_info* ti = &g_tests[desc->test];
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    DeviceInfo di;
+    if (int rc = probe_device(dev, &di)) return rc;
+    b200_sweep_desc d = *desc;
+    HostArgs a{&d, arrays, (cudaStream_t)stream, dev, di.num_sms};
+    for (int it = 0; it < niters; it++) {
+        d.reverse_order = (desc->reverse_order + it) & 1;
+        if (int rc = g_launch[desc->test](desc->dtype, a)) return rc;
+        // the reference driver's rotation: laplacian.c:299-300 (swap), wave13pt.c:919-920 (3-cycle)
+        if (ti->rotation == 2) { void* w = arrays[0]; arrays[0] = arrays[1]; arrays[1] = w; }
+        else if (ti->rotation == 3) { void* w = arrays[0]; arrays[0] = arrays[1]; arrays[1] = arrays[2]; arrays[2] = w; }
+    }
+    return B200_OK;
+}
+
 int b200_kernel_info(int test, int dtype, int* regs_per_thread, const char** kernel_name)
 {
     if (test < 0 || test >= B200_NTESTS) { set_error("unknown test id %d", test); return B200_ERR_ARG; }
@@ -535,6 +557,7 @@ int b200_run(b200_ctx* c, int niters, b200_stats* stats)
             else if (ti->ndims == 3) d.ns = mem_n;
             else d.ny = mem_n;
             memcpy(d.scalars, c->sc, sizeof(d.scalars));
+            d.reverse_order = it & 1;
             // output range: owned planes inside the global interior, in local coordinates
             const int split_dim = ti->ndims == 3 ? 2 : 1;
             int lo = s.own_lo, hi = s.own_hi;

@@ -66,6 +66,22 @@ B200_DEV void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
         : "memory");
 }
 
+// L2 cache-policy descriptors for the .L2::cache_hint operand (same encodings CUTLASS uses)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST  = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST   = 0x14F0000000000000ull;
+
+B200_DEV void tma_load_3d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                               uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+          "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+
 // ---- vector types -----------------------------------------------------------------
 template <typename T> struct Vec;            // 16-byte vector of T
 template <> struct Vec<float>  { using type = float4;  static constexpr int N = 4; };

@@ -79,6 +79,7 @@ template <class Op> int launch_stream(const HostArgs& a)
     StreamParams P{};
     TensorMaps M{};
     P.nx = d.nx; P.ny = d.ny; P.ns = (ti->ndims == 3) ? d.ns : 1;
+    P.nxny = (long long)d.nx * d.ny;
     P.xlo = ti->lo[0]; P.xhi = P.nx - ti->hi[0];
     P.ylo = ti->lo[1]; P.yhi = P.ny - ti->hi[1];
     if (ti->ndims == 3) { P.z0 = ti->lo[2]; P.z1 = P.ns - ti->hi[2]; }
@@ -106,6 +107,10 @@ template <class Op> int launch_stream(const HostArgs& a)
     P.use_tma = aligned && !no_tma;
     P.vec_ok = aligned;
 
+    static const int env_cs = getenv("B200_STORE_CS") ? atoi(getenv("B200_STORE_CS")) : 0;
+    static const int env_serp = getenv("B200_SERPENTINE") ? atoi(getenv("B200_SERPENTINE")) : 1;
+    P.store_cs = env_cs || ti->rotation == 0;   // divergence / gradient outputs are never read back: stream them past the L2
+    P.reverse = env_serp ? (d.reverse_order & 1) : 0;
     P.push_slot = -1;
     P.push_dim = ti->ndims == 3 ? 2 : 1;
     if (d.push_lo || d.push_hi) {

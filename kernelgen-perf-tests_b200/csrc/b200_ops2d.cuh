@@ -16,7 +16,7 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct JacobiOp {
     using real = T;
-    static constexpr int TX = 128, TY = 32, STAGES = 3, HOLD = 0, WARM = 0, MIN_BLOCKS = 2;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 0, 0}; }
     using G = Geo<JacobiOp>;
@@ -55,7 +55,7 @@ template <typename T> struct JacobiOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct GaussblurOp {
     using real = T;
-    static constexpr int TX = 128, TY = 32, STAGES = 3, HOLD = 0, WARM = 0, MIN_BLOCKS = 2;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 2, 2, 0, 0}; }
     using G = Geo<GaussblurOp>;
@@ -111,7 +111,7 @@ template <typename T> struct GaussblurOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct GameoflifeOp {
     using real = T;
-    static constexpr int TX = 128, TY = 32, STAGES = 3, HOLD = 0, WARM = 0, MIN_BLOCKS = 2;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 0, 0}; }
     using G = Geo<GameoflifeOp>;

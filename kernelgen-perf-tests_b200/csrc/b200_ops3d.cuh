@@ -19,7 +19,7 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct LaplacianOp {
     using real = T;
-    static constexpr int TX = 128, TY = 16, STAGES = 4, HOLD = 0, WARM = 2, MIN_BLOCKS = 2;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 48 : 24), STAGES = 6, HOLD = 0, WARM = 2, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
     using G = Geo<LaplacianOp>;
@@ -65,12 +65,12 @@ template <typename T> struct LaplacianOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct Wave13ptOp {
     using real = T;
-    static constexpr int TX = 128, TY = 8, STAGES = 4, HOLD = 0, WARM = 4, MIN_BLOCKS = 2;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 6, HOLD = 0, WARM = 4, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 2;
     static constexpr StagedSpec spec(int a)
     {
         return a == 0 ? StagedSpec{1, 1, 2, 2, 2, 2}     // w1: radius-2 halo, arrives 2 planes ahead
-                      : StagedSpec{0, 0, 0, 0, 0, 0};    // w0: point-wise, plane s
+                      : StagedSpec{0, 0, 0, 0, 0, 0, 1}; // w0: point-wise, plane s; overwritten by the next sweep
     }
     using G = Geo<Wave13ptOp>;
     static constexpr int V = G::V, CPT = G::CPT;
@@ -121,7 +121,7 @@ template <typename T> struct Wave13ptOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct DivergenceOp {
     using real = T;
-    static constexpr int TX = 128, TY = 8, STAGES = 4, HOLD = 0, WARM = 2, MIN_BLOCKS = 2;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 5, HOLD = 0, WARM = 2, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 3;
     static constexpr StagedSpec spec(int a)
     {
@@ -169,7 +169,7 @@ template <typename T> struct DivergenceOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct GradientOp {
     using real = T;
-    static constexpr int TX = 128, TY = 16, STAGES = 4, HOLD = 0, WARM = 2, MIN_BLOCKS = 2;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 8, HOLD = 0, WARM = 2, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
     using G = Geo<GradientOp>;
@@ -219,11 +219,11 @@ template <typename T> struct GradientOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct Uxx1Op {
     using real = T;
-    static constexpr int TX = 128, TY = 8, STAGES = 4, HOLD = 0, WARM = 3, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 12 : 6), STAGES = 5, HOLD = 0, WARM = 3, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 5;
     static constexpr StagedSpec spec(int a)
     {
-        return a == 0 ? StagedSpec{0, 0, 0, 0, 0, 0}     // u0: point-wise, plane s
+        return a == 0 ? StagedSpec{0, 0, 0, 0, 0, 0, 1}  // u0: point-wise, plane s; overwritten by the next sweep
              : a == 1 ? StagedSpec{2, 0, 1, 0, 0, 1}     // d1: rows j-1..j, planes s-1..s
              : a == 2 ? StagedSpec{3, 1, 0, 0, 0, 0}     // xx: x-2..x+1, plane s
              : a == 3 ? StagedSpec{4, 0, 2, 1, 0, 0}     // xy: rows j-2..j+1, plane s
@@ -289,7 +289,7 @@ template <typename T> struct Uxx1Op {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct LapgsrbOp {
     using real = T;
-    static constexpr int TX = 128, TY = 8, STAGES = 4, HOLD = 0, WARM = 4, MIN_BLOCKS = 2;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 8, HOLD = 0, WARM = 4, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 2, 2, 2, 2}; }
     using G = Geo<LapgsrbOp>;
@@ -363,7 +363,7 @@ template <typename T> B200_DEV void cubic_weights(T t, T (&w)[4])
 
 template <typename T> struct TricubicOp {
     using real = T;
-    static constexpr int TX = 128, TY = 8, STAGES = 6, HOLD = 3, WARM = 3, MIN_BLOCKS = 2;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 8, HOLD = 3, WARM = 3, MIN_BLOCKS = 1;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 2, 2, 1}; }
     using G = Geo<TricubicOp>;

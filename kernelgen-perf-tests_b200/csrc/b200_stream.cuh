@@ -25,7 +25,7 @@
 
 namespace b200 {
 
-constexpr int NCONS = 256;              // consumer threads (8 warps)
+constexpr int NCONS = 384;              // consumer threads (12 warps), one CTA per SM
 constexpr int NTHREADS = NCONS + 32;    // + 1 producer warp
 constexpr int MAX_STAGED = 5;
 constexpr int MAX_STAGES = 8;           // 2*MAX_STAGES mbarriers fit the 128-byte header
@@ -38,10 +38,14 @@ struct StagedSpec {
     int yhi;
     int lead;   // at the step that emits output plane s, plane s+lead of this array arrives
     int zlo;    // deepest plane below the output plane that is needed (s - zlo)
+    int dead;   // 1: the buffer is overwritten by the NEXT sweep (rotation), so what this sweep reads
+                //    from it is dead afterwards: load with L2 evict-first and leave the L2 to the
+                //    arrays the next sweep will read again
 };
 
 struct StreamParams {
     int nx, ny, ns;                 // array extents
+    long long nxny;                 // nx * ny (elements per plane)
     int xlo, xhi, ylo, yhi;         // output box (half-open), x and y
     int z0, z1;                     // output planes
     int ntx, nty, nzc, zc_len;      // work decomposition
@@ -55,6 +59,8 @@ struct StreamParams {
     void* push_hi; int push_hi_src, push_hi_dst, push_hi_cnt;
     int push_slot;
     int push_dim;                   // 2: planes (3D tests), 1: rows (2D tests)
+    int store_cs;                   // 1: streaming (evict-first) stores
+    int reverse;                    // 1: walk the items in reverse order (serpentine sweeps)
 };
 
 struct alignas(64) TensorMaps {
@@ -90,50 +96,67 @@ template <class Op> struct Geo {
     static_assert(Op::STAGES > Op::HOLD, "ring too shallow");
 };
 
-// What Op::step() sees.
+// What Op::step() sees.  Everything that is invariant over an item (tile) or a step is computed
+// once there, so a store costs a row test, one multiply-add and the address add.
 template <class Op> struct Ctx {
     using T = typename Op::real;
     using G = Geo<Op>;
     const StreamParams& P;
     unsigned char* stages;      // base of the ring
-    uint32_t g;                 // global step counter (ring position)
+    uint32_t st;                // ring stage of this step
     int X0, Y0;                 // global x of tile column 0, global y of tile row 0
     int s;                      // output plane of this step
     int rel;                    // s - (first output plane of the item); < 0 during warm-up
     int tx, ty;                 // consumer thread coordinates
+    int x;                      // global x of this thread's vector (per item)
+    int xmode;                  // per item: 1 = whole vector inside [xlo,xhi) and 16-byte stores legal,
+                                //           2 = some elements inside, 0 = none
+    unsigned yspan;             // yhi - ylo
+
+    B200_DEV void begin_item(int X0_, int Y0_)
+    {
+        X0 = X0_;
+        Y0 = Y0_;
+        x = X0 + G::V * tx;
+        const bool some = x + G::V > P.xlo && x < P.xhi;
+        const bool all = x >= P.xlo && x + G::V <= P.xhi;
+        xmode = (all && P.vec_ok) ? 1 : (some ? 2 : 0);
+        yspan = (unsigned)(P.yhi - P.ylo);
+    }
 
     // Pointer to this thread's 16-byte vector in tile row `row` (tile-local output row, may be
     // negative / >= TY inside the halo) of staged array A, in the stage loaded `back` steps ago.
     template <int A> B200_DEV const T* tile(int row, int back = 0) const
     {
-        const uint32_t st = (g - (uint32_t)back) % (uint32_t)Op::STAGES;
-        const T* base = reinterpret_cast<const T*>(stages + st * G::STAGE_BYTES + G::arr_off(A));
+        uint32_t q = st;
+        if (back) q = (st + (uint32_t)Op::STAGES - (uint32_t)back) % (uint32_t)Op::STAGES;
+        const T* base = reinterpret_cast<const T*>(stages + q * G::STAGE_BYTES + G::arr_off(A));
         return base + (row + Op::spec(A).ylo) * G::bw(A) + G::hxp(A) + G::V * tx;
     }
-    B200_DEV int gx() const { return X0 + G::V * tx; }
+    B200_DEV int gx() const { return x; }
 
     // Read-only pointer into a global array at (x of this thread, tile row, plane).
     template <int SLOT> B200_DEV const T* gptr(int row, int plane) const
     {
         const T* a = reinterpret_cast<const T*>(P.arr[SLOT]);
-        return a + ((size_t)plane * P.ny + (size_t)(Y0 + row)) * P.nx + gx();
+        return a + ((size_t)plane * P.ny + (size_t)(Y0 + row)) * P.nx + x;
     }
     // true when this thread's whole 16-byte vector at (row, any plane) is inside the array
     B200_DEV bool vec_in_array(int row) const
     {
-        return P.vec_ok && gx() + G::V <= P.nx && (Y0 + row) >= 0 && (Y0 + row) < P.ny;
+        return P.vec_ok && x + G::V <= P.nx && (Y0 + row) >= 0 && (Y0 + row) < P.ny;
     }
 
     // 16-byte (or element-predicated) store of V values at (x of this thread, y, plane) of array a
     B200_DEV void store_vec(T* a, int y, int plane, const T (&val)[G::V]) const
     {
-        const int x = gx();
-        T* dst = a + ((size_t)plane * P.ny + (size_t)y) * P.nx + x;
-        if (P.vec_ok && x >= P.xlo && x + G::V <= P.xhi) {
+        T* dst = a + ((size_t)plane * P.nxny + (size_t)(y * P.nx + x));
+        if (xmode == 1) {
             VReg<T> r;
 #pragma unroll
             for (int v = 0; v < G::V; v++) r[v] = val[v];
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(r.v);
+            if (P.store_cs) __stcs(reinterpret_cast<uint4*>(dst), *reinterpret_cast<const uint4*>(r.v));
+            else *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(r.v);
         } else {
 #pragma unroll
             for (int v = 0; v < G::V; v++)
@@ -145,7 +168,7 @@ template <class Op> struct Ctx {
     template <int SLOT> B200_DEV void store(int row, int plane, const T (&val)[G::V]) const
     {
         const int y = Y0 + row;
-        if (y < P.ylo || y >= P.yhi) return;
+        if ((unsigned)(y - P.ylo) >= yspan || xmode == 0) return;
         store_vec(reinterpret_cast<T*>(P.arr[SLOT]), y, plane, val);
         if (SLOT == P.push_slot) {
             // fused halo push: the same values also go to the neighbour GPU's ghost planes (rows for
@@ -197,8 +220,9 @@ template <class Op, int A> struct ProducerIssue {
     {
         if constexpr (A < Op::NSTAGED) {
             if (s + Op::spec(A).lead >= za - Op::spec(A).zlo)
-                tma_load_3d(stage + Geo<Op>::arr_off(A), &M.m[A], bar, X0 - Geo<Op>::hxp(A),
-                            Y0 - Op::spec(A).ylo, s + Op::spec(A).lead);
+                tma_load_3d_hint(stage + Geo<Op>::arr_off(A), &M.m[A], bar, X0 - Geo<Op>::hxp(A),
+                                 Y0 - Op::spec(A).ylo, s + Op::spec(A).lead,
+                                 Op::spec(A).dead ? L2_EVICT_FIRST : L2_EVICT_NORMAL);
             ProducerIssue<Op, A + 1>::tma(M, stage, bar, X0, Y0, s, za);
         }
     }
@@ -217,6 +241,7 @@ struct ItemCoords { int X0, Y0, za, zb; };
 template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int item)
 {
     const int tiles_xy = P.ntx * P.nty;
+    if (P.reverse) item = P.nitems - 1 - item;
     const int zc = item / tiles_xy;
     const int t = item - zc * tiles_xy;
     const int tyi = t / P.ntx, txi = t - tyi * P.ntx;
@@ -228,8 +253,15 @@ template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int i
     return c;
 }
 
+// One CTA per SM: 12 consumer warps + the producer warp.  The register file is split over the
+// four SM sub-partitions (16384 registers each) and warps are dealt round-robin, so 13 warps
+// (4+3+3+3) can have the full 128 registers per thread, while 16+1 warps or 2 CTAs x (8+1) warps
+// put 5 warps on one sub-partition and are limited to 96 -- which spills in every double kernel
+// (measured: profiles/README.md).
+template <class Op> struct RegCap { static constexpr int value = 128; };
+
 template <class Op>
-__global__ void __launch_bounds__(NTHREADS, Op::MIN_BLOCKS)
+__global__ void __launch_bounds__(NTHREADS) __maxnreg__(RegCap<Op>::value)
 stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ TensorMaps M)
 {
     using G = Geo<Op>;
@@ -284,16 +316,15 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
         // ------------------------------ consumer warps ------------------------------
         Op op(P);
         typename Op::State state;
-        Ctx<Op> ctx{P, stages, 0u, 0, 0, 0, 0, tid % G::LX, tid / G::LX};
+        Ctx<Op> ctx{P, stages, 0u, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0u};
+        uint32_t st = 0, ph = 0, rel_st = (uint32_t)(S - Op::HOLD) % S;    // ring stage / phase of this step; stage to hand back
         uint32_t g = 0;
         for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
             const ItemCoords c = decode_item<Op>(P, item);
-            ctx.X0 = c.X0;
-            ctx.Y0 = c.Y0;
+            ctx.begin_item(c.X0, c.Y0);
             int local = 0;
             for (int s = c.za - Op::WARM; s < c.zb; ++s, ++g, ++local) {
-                const uint32_t st = g % S, ph = (g / S) & 1u;
-                ctx.g = g;
+                ctx.st = st;
                 ctx.s = s;
                 ctx.rel = s - c.za;
                 op.pre(ctx, state);
@@ -301,8 +332,10 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
                 op.step(ctx, state);
                 if (local >= Op::HOLD) {
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[(g - (uint32_t)Op::HOLD) % S]);
+                    if (lane == 0) mbar_arrive(&empty[rel_st]);
                 }
+                if (++st == S) { st = 0; ph ^= 1u; }
+                if (++rel_st == S) rel_st = 0;
             }
             if constexpr (Op::HOLD > 0) {
                 // hand back the stages still held at the end of the item
