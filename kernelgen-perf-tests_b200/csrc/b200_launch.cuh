@@ -87,8 +87,13 @@ template <class Op> int launch_stream(const HostArgs& a)
     if (d.out_begin != 0 || d.out_end != 0) {
         int& lo = (ti->ndims == 3) ? P.z0 : P.ylo;
         int& hi = (ti->ndims == 3) ? P.z1 : P.yhi;
-        if (d.out_begin < lo || d.out_end > hi || d.out_begin > d.out_end) {
-            set_error("%s: output range [%d,%d) outside the interior [%d,%d)", ti->name, d.out_begin, d.out_end, lo, hi);
+        // a slab may start output wherever the stencil's reach (= ghost depth) stays inside the local array;
+        // for the whole grid that is the interior, except tricubic2 whose interior is one plane narrower
+        const int n_split = (ti->ndims == 3) ? P.ns : P.ny;
+        const int rlo = ti->zghost_lo, rhi = n_split - ti->zghost_hi;
+        if (d.out_begin < rlo || d.out_end > rhi || d.out_begin > d.out_end) {
+            set_error("%s: output range [%d,%d) reaches outside the local array, allowed [%d,%d)", ti->name,
+                      d.out_begin, d.out_end, rlo, rhi);
             return B200_ERR_ARG;
         }
         lo = d.out_begin; hi = d.out_end;

@@ -263,6 +263,28 @@ class SlabEngine:
                 self.idxs = [self.idxs[1], self.idxs[2], self.idxs[0]]
             self.sweeps_done += 1
 
+    # -- scatter / gather of a global host array (tests) ---------------------------------------
+    def set_global(self, q: int, full: np.ndarray):
+        """Load this rank's slab (owned planes + ghosts) of slot q from the GLOBAL array."""
+        L, torch = self.layout, self.torch
+        if self.test == "matvec":
+            part = {0: full[L.mem_lo * self.nx:L.mem_hi * self.nx], 1: full, 2: full[L.mem_lo:L.mem_hi]}[q]
+        else:
+            part = full[L.mem_lo * self.unit:L.mem_hi * self.unit]
+        self.t[q].copy_(torch.from_numpy(np.ascontiguousarray(part)).to(self.t[q].device))
+
+    def get_owned(self, q: int) -> np.ndarray:
+        """This rank's OWNED planes of slot q (no ghosts), as a host array."""
+        L = self.layout
+        if self.test == "matvec":
+            if q == 1:
+                return self.t[q].cpu().numpy()
+            u = self.nx if q == 0 else 1
+        else:
+            u = self.unit
+        a, b = (L.own_lo - L.mem_lo) * u, (L.own_hi - L.mem_lo) * u
+        return self.t[q][a:b].cpu().numpy()
+
     def result_slot(self):
         if self.info["rotation"]:
             return self.idxs[1]

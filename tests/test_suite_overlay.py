@@ -1,0 +1,56 @@
+"""CPU test of the suite wiring: the overlay installs a `b200` target
+into a writable checkout of the reference suite, `make <test>.b200` builds the driver there, and
+the reference's own `benchmark` script discovers the target, runs it and parses its output.
+Needs the reference tree (present in the build container only) -- skipped elsewhere.  Without a
+GPU the b200 rows show FAIL for t_comp / f_mean (the driver exits loudly: no CPU fallback), but
+the i_mean column must already agree with the gcc row: same rand() order, same printf."""
+import re
+import shutil
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not REF.is_dir(), reason="reference suite not present")
+def test_overlay_install_build_and_benchmark(tmp_path, pkg):
+    pkg.load()
+    suite = tmp_path / "suite"
+    shutil.copytree(REF, suite, symlinks=True)
+    subprocess.run(["chmod", "-R", "u+w", str(suite)], check=True)
+    inst = ROOT / "kernelgen-perf-tests_b200" / "suite_overlay" / "install_overlay.sh"
+    subprocess.run(["sh", str(inst), str(suite), str(ROOT)], check=True, capture_output=True)
+    for t in ("laplacian", "wave13pt", "jacobi", "gameoflife", "tricubic2", "matvec"):
+        assert (suite / t / "b200" / "makefile").exists()
+        assert (suite / t / "b200" / "kernel").read_text() == t
+    bench = (suite / "benchmark").read_text()
+    assert bench.count('($target eq "b200")') == 4            # benchmark:126,162,174,210
+    # idempotent
+    subprocess.run(["sh", str(inst), str(suite), str(ROOT)], check=True, capture_output=True)
+    assert (suite / "benchmark").read_text() == bench
+    subprocess.run(["make", "-s", "laplacian.b200", "laplacian.gcc", "gameoflife.b200", "gameoflife.gcc"],
+                   cwd=suite, check=True, capture_output=True)
+    assert (suite / "laplacian" / "b200" / "laplacian").exists()
+    out = subprocess.run(["./benchmark", "16", "8", "8", "1", "1", "b200", "gcc"], cwd=suite,
+                         capture_output=True, text=True).stdout
+    assert "Found test laplacian" in out
+    rows = {}
+    for line in out.splitlines():
+        m = re.match(r"\|\s*(\w+)\s*\|\s*(\w+)\s*\|\s*(\S+)\s*\|", line)
+        if m and m.group(2) in ("b200", "gcc"):
+            rows[(m.group(1), m.group(2))] = [c.strip() for c in line.strip("|").split("|")]
+    for t in ("laplacian", "gameoflife"):
+        assert rows[(t, "b200")][2] == rows[(t, "gcc")][2]     # i_mean column
+        if not _have_gpu():
+            assert rows[(t, "b200")][6] == "FAIL"             # t_comp: driver refused to run without a GPU
