@@ -15,7 +15,7 @@
 
 namespace b200 {
 
-template <class Op> struct KernelSetup {
+template <class Op, bool PUSH> struct KernelSetup {
     bool done[16] = {};
     int blocks_per_sm[16] = {};
     std::mutex mu;
@@ -24,10 +24,10 @@ template <class Op> struct KernelSetup {
         std::lock_guard<std::mutex> lk(mu);
         if (device < 0 || device >= 16) { set_error("device index %d out of range", device); return B200_ERR_ARG; }
         if (!done[device]) {
-            B200_CUDA(cudaFuncSetAttribute(stream_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            B200_CUDA(cudaFuncSetAttribute(stream_kernel<Op, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Geo<Op>::SMEM_BYTES));
             int n = 0;
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stream_kernel<Op>, NTHREADS,
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stream_kernel<Op, PUSH>, NTHREADS,
                                                                     Geo<Op>::SMEM_BYTES));
             if (n < 1) { set_error("kernel does not fit on an SM"); return B200_ERR_CUDA; }
             blocks_per_sm[device] = n;
@@ -38,9 +38,9 @@ template <class Op> struct KernelSetup {
     }
 };
 
-template <class Op> KernelSetup<Op>& kernel_setup()
+template <class Op, bool PUSH> KernelSetup<Op, PUSH>& kernel_setup()
 {
-    static KernelSetup<Op> s;
+    static KernelSetup<Op, PUSH> s;
     return s;
 }
 
@@ -73,8 +73,9 @@ template <class Op> int launch_stream(const HostArgs& a)
     const b200_sweep_desc& d = *a.desc;
     const b200_test_info* ti = b200_get_test_info(d.test);
 
+    const bool push = d.push_lo || d.push_hi;
     int bps = 0;
-    if (int rc = kernel_setup<Op>().get(a.device, &bps)) return rc;
+    if (int rc = push ? kernel_setup<Op, true>().get(a.device, &bps) : kernel_setup<Op, false>().get(a.device, &bps)) return rc;
 
     StreamParams P{};
     TensorMaps M{};
@@ -112,9 +113,7 @@ template <class Op> int launch_stream(const HostArgs& a)
     P.use_tma = aligned && !no_tma;
     P.vec_ok = aligned;
 
-    static const int env_cs = getenv("B200_STORE_CS") ? atoi(getenv("B200_STORE_CS")) : 0;
     static const int env_serp = getenv("B200_SERPENTINE") ? atoi(getenv("B200_SERPENTINE")) : 1;
-    P.store_cs = env_cs || ti->rotation == 0;   // divergence / gradient outputs are never read back: stream them past the L2
     P.reverse = env_serp ? (d.reverse_order & 1) : 0;
     P.push_slot = -1;
     P.push_dim = ti->ndims == 3 ? 2 : 1;
@@ -143,7 +142,8 @@ template <class Op> int launch_stream(const HostArgs& a)
     }
 
     const int grid = (int)(items < grid_cap ? items : grid_cap);
-    stream_kernel<Op><<<grid, NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
+    if (push) stream_kernel<Op, true><<<grid, NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
+    else stream_kernel<Op, false><<<grid, NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
     B200_CUDA(cudaGetLastError());
     count_launch();
     return B200_OK;
@@ -152,13 +152,13 @@ template <class Op> int launch_stream(const HostArgs& a)
 template <class Op> int info_stream(KernelInfo* ki, const char* name)
 {
     cudaFuncAttributes fa;
-    B200_CUDA(cudaFuncGetAttributes(&fa, stream_kernel<Op>));
+    B200_CUDA(cudaFuncGetAttributes(&fa, stream_kernel<Op, false>));
     ki->regs = fa.numRegs;
     ki->smem_bytes = Geo<Op>::SMEM_BYTES;
     ki->name = name;
     int dev = 0, bps = 0;
     B200_CUDA(cudaGetDevice(&dev));
-    if (int rc = kernel_setup<Op>().get(dev, &bps)) return rc;
+    if (int rc = kernel_setup<Op, false>().get(dev, &bps)) return rc;
     ki->blocks_per_sm = bps;
     return B200_OK;
 }

@@ -16,7 +16,8 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct JacobiOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 0, 0}; }
     using G = Geo<JacobiOp>;
@@ -24,8 +25,8 @@ template <typename T> struct JacobiOp {
     struct State { };
     T c0, c1, c2;
     B200_DEV JacobiOp(const StreamParams& P) : c0((T)P.sc[0]), c1((T)P.sc[1]), c2((T)P.sc[2]) {}
-    B200_DEV void pre(const Ctx<JacobiOp>&, State&) {}
-    B200_DEV void step(const Ctx<JacobiOp>& ctx, State&)
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State&)
     {
         constexpr int BW = G::bw(0);
         const int r0 = ctx.ty * CPT;
@@ -42,7 +43,7 @@ template <typename T> struct JacobiOp {
                 o[v] = c0 * wc.at(v, 0) +
                        c1 * (((wc.at(v, -1) + wm.at(v, 0)) + wc.at(v, 1)) + wp.at(v, 0)) +
                        c2 * (((wm.at(v, -1) + wp.at(v, -1)) + wm.at(v, 1)) + wp.at(v, 1));
-            ctx.template store<1>(r0 + r, 0, o);
+            ctx.template store<1>(r0 + r, o);
             wm = wc;
             wc = wp;
         }
@@ -55,7 +56,8 @@ template <typename T> struct JacobiOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct GaussblurOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 2, 2, 0, 0}; }
     using G = Geo<GaussblurOp>;
@@ -67,8 +69,8 @@ template <typename T> struct GaussblurOp {
     {
         f = (T)(1. / (double)(s0 + 4 * (s1 + s2 + s4 + s8) + 8 * s5));
     }
-    B200_DEV void pre(const Ctx<GaussblurOp>&, State&) {}
-    B200_DEV void step(const Ctx<GaussblurOp>& ctx, State&)
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State&)
     {
         constexpr int BW = G::bw(0);
         const int r0 = ctx.ty * CPT;
@@ -92,7 +94,7 @@ template <typename T> struct GaussblurOp {
                     s5 * (((((((b.at(v, -2) + a.at(v, -1)) + a.at(v, 1)) + b.at(v, 2)) +
                              d.at(v, -2)) + e.at(v, -1)) + e.at(v, 1)) + d.at(v, 2)) +
                     s8 * (((a.at(v, -2) + a.at(v, 2)) + e.at(v, -2)) + e.at(v, 2)));
-            ctx.template store<1>(r0 + r, 0, o);
+            ctx.template store<1>(r0 + r, o);
             a = b;
             b = c;
             c = d;
@@ -111,21 +113,22 @@ template <typename T> struct GaussblurOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct GameoflifeOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 0, 0}; }
     using G = Geo<GameoflifeOp>;
     static constexpr int V = G::V, CPT = G::CPT;
     struct State { };
-    double C;
-    B200_DEV GameoflifeOp(const StreamParams&) { C = (double)(T)100000000000000000000.; }
-    B200_DEV void pre(const Ctx<GameoflifeOp>&, State&) {}
+    double Cbig;
+    B200_DEV GameoflifeOp(const StreamParams&) { Cbig = (double)(T)100000000000000000000.; }
+    template <class C> B200_DEV void pre(const C&, State&) {}
     B200_DEV static T add(T a, T b)
     {
         if constexpr (sizeof(T) == 4) return __fadd_rn(a, b);
         else return __dadd_rn(a, b);
     }
-    B200_DEV void step(const Ctx<GameoflifeOp>& ctx, State&)
+    template <int PH, class C> B200_DEV void step(const C& ctx, State&)
     {
         constexpr int BW = G::bw(0);
         const int r0 = ctx.ty * CPT;
@@ -148,10 +151,10 @@ template <typename T> struct GameoflifeOp {
                 L = add(L, wp.at(v, 1));
                 const double x = __dadd_rn((double)add(wc.at(v, 0), L), -3.);
                 const double y = __dadd_rn((double)L, -3.);
-                const double den = __dadd_rn(1., __dmul_rn(__dmul_rn(x, y), C));
+                const double den = __dadd_rn(1., __dmul_rn(__dmul_rn(x, y), Cbig));
                 o[v] = (T)__ddiv_rn(1., den);
             }
-            ctx.template store<1>(r0 + r, 0, o);
+            ctx.template store<1>(r0 + r, o);
             wm = wc;
             wc = wp;
         }

@@ -3,9 +3,10 @@
 // Every Op marches in z (2.5D): at the step that emits output plane s the ring stage holds
 // plane s+lead of each staged input.  In-plane (x,y) neighbours are read from shared memory the
 // moment a plane arrives and folded into per-thread partial sums; z neighbours live in
-// per-thread register queues.  Reference formulas are cited per Op (file:line under the
-// reference tree); evaluation order follows the reference where that is free, otherwise the
-// re-association is noted (covered by the stated normwise tolerance).
+// per-thread REGISTER RINGS indexed by the compile-time phase PH = (step in item) mod PERIOD, so
+// advancing the queue costs no register moves.  Reference formulas are cited per Op (file:line
+// under the reference tree); evaluation order follows the reference where that is free,
+// otherwise the re-association is noted (covered by the stated normwise tolerance).
 #pragma once
 
 #include "b200_stream.cuh"
@@ -16,19 +17,23 @@ namespace b200 {
 
 // ------------------------------------------------------------------------------------------
 // laplacian: w1 = alpha*w0 + beta*(x+1 + x-1 + y+1 + y-1 + z+1 + z-1)     laplacian/laplacian.c:93-97
+// Accumulate-forward form: when plane p arrives, acc_p = alpha*C_p + beta*(inplane_p + C_{p-1}) is
+// formed and out_{p-1} = acc_{p-1} + beta*C_p is emitted: two live values per point, no queue.
+// (beta is distributed over the z+1 term: a re-association.)
 // ------------------------------------------------------------------------------------------
 template <typename T> struct LaplacianOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 48 : 24), STAGES = 6, HOLD = 0, WARM = 2, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 48 : 24), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 1;
+    static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
     using G = Geo<LaplacianOp>;
     static constexpr int V = G::V, CPT = G::CPT;
-    struct State { T cm[CPT][V], c0[CPT][V], ip[CPT][V]; };
+    struct State { T acc[CPT][V], cp[CPT][V]; };
     T alpha, beta;
     B200_DEV LaplacianOp(const StreamParams& P) : alpha((T)P.sc[0]), beta((T)P.sc[1]) {}
-    B200_DEV void pre(const Ctx<LaplacianOp>&, State&) {}
-    B200_DEV void step(const Ctx<LaplacianOp>& ctx, State& S)
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State& S)
     {
         constexpr int BW = G::bw(0);
         B200_UNROLL
@@ -38,21 +43,17 @@ template <typename T> struct LaplacianOp {
             Window<1, 1, T> w;
             w.load(p);
             const VReg<T> up = ldv(p + BW), dn = ldv(p - BW);
-            T ipn[V];
-            B200_UNROLL
-            for (int v = 0; v < V; v++) ipn[v] = ((w.at(v, 1) + w.at(v, -1)) + up[v]) + dn[v];
             if (ctx.rel >= 0) {
                 T o[V];
                 B200_UNROLL
-                for (int v = 0; v < V; v++)
-                    o[v] = alpha * S.c0[c][v] + beta * ((S.ip[c][v] + w.at(v, 0)) + S.cm[c][v]);
-                ctx.template store<1>(row, ctx.s, o);
+                for (int v = 0; v < V; v++) o[v] = S.acc[c][v] + beta * w.at(v, 0);
+                ctx.template store<1>(row, o);
             }
             B200_UNROLL
             for (int v = 0; v < V; v++) {
-                S.cm[c][v] = S.c0[c][v];
-                S.c0[c][v] = w.at(v, 0);
-                S.ip[c][v] = ipn[v];
+                const T ip = ((w.at(v, 1) + w.at(v, -1)) + up[v]) + dn[v];
+                S.acc[c][v] = alpha * w.at(v, 0) + beta * (ip + S.cp[c][v]);
+                S.cp[c][v] = w.at(v, 0);
             }
         }
     }
@@ -61,26 +62,33 @@ template <typename T> struct LaplacianOp {
 // ------------------------------------------------------------------------------------------
 // wave13pt: w2 = m0*w1 - w0 + m1*(6 radius-1 nbrs of w1) + m2*(6 radius-2 nbrs of w1)
 //                                                                  wave13pt/wave13pt.c:640-651
-// m1, m2 are distributed over the in-plane and the z parts of their sums (re-association).
+// Accumulate-forward form (m1, m2 distributed over their sums: a re-association).  When plane
+// p = s+2 of w1 arrives:
+//     out_s      = acc_s + m2*C_p - w0_s                                   (emitted)
+//     acc_{s+1} += m1*C_p
+//     acc_p      = m0*C_p + inplane_p + m1*C_{p-1} + m2*C_{p-2}
+// rings of two: acc[PH&1] = acc_s, acc[(PH+1)&1] = acc_{s+1}; Cq[PH&1] = C_s, Cq[(PH+1)&1] = C_{s+1}.
 // ------------------------------------------------------------------------------------------
 template <typename T> struct Wave13ptOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 6, HOLD = 0, WARM = 4, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 6, HOLD = 0, WARM = 4, PERIOD = 2;
+    static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 2;
     static constexpr StagedSpec spec(int a)
     {
-        return a == 0 ? StagedSpec{1, 1, 2, 2, 2, 2}     // w1: radius-2 halo, arrives 2 planes ahead
-                      : StagedSpec{0, 0, 0, 0, 0, 0, 1}; // w0: point-wise, plane s; overwritten by the next sweep
+        return a == 0 ? StagedSpec{1, 1, 2, 2, 2, 2}      // w1: radius-2 halo, arrives 2 planes ahead
+                      : StagedSpec{0, 0, 0, 0, 0, 0, 1};  // w0: point-wise, plane s; overwritten by the next sweep
     }
     using G = Geo<Wave13ptOp>;
     static constexpr int V = G::V, CPT = G::CPT;
-    struct State { T q[CPT][4][V]; T pend[CPT][2][V]; };
+    struct State { T acc[2][CPT][V]; T Cq[2][CPT][V]; };
     T m0, m1, m2;
     B200_DEV Wave13ptOp(const StreamParams& P) : m0((T)P.sc[0]), m1((T)P.sc[1]), m2((T)P.sc[2]) {}
-    B200_DEV void pre(const Ctx<Wave13ptOp>&, State&) {}
-    B200_DEV void step(const Ctx<Wave13ptOp>& ctx, State& S)
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State& S)
     {
         constexpr int BW = G::bw(0);
+        constexpr int A0 = PH & 1, A1 = (PH + 1) & 1;
         B200_UNROLL
         for (int c = 0; c < CPT; c++) {
             const int row = ctx.ty + G::LY * c;
@@ -88,28 +96,22 @@ template <typename T> struct Wave13ptOp {
             Window<2, 2, T> w;
             w.load(p);
             const VReg<T> u1 = ldv(p + BW), d1 = ldv(p - BW), u2 = ldv(p + 2 * BW), d2 = ldv(p - 2 * BW);
-            T pn[V];
-            B200_UNROLL
-            for (int v = 0; v < V; v++)
-                pn[v] = m1 * (((w.at(v, 1) + w.at(v, -1)) + u1[v]) + d1[v]) +
-                        m2 * (((w.at(v, 2) + w.at(v, -2)) + u2[v]) + d2[v]);
             if (ctx.rel >= 0) {
                 const VReg<T> w0 = ldv(ctx.template tile<1>(row));   // w0 plane s
                 T o[V];
                 B200_UNROLL
-                for (int v = 0; v < V; v++)
-                    o[v] = (m0 * S.q[c][2][v] - w0[v]) + S.pend[c][0][v] +
-                           m1 * (S.q[c][3][v] + S.q[c][1][v]) + m2 * (w.at(v, 0) + S.q[c][0][v]);
-                ctx.template store<2>(row, ctx.s, o);
+                for (int v = 0; v < V; v++) o[v] = (S.acc[A0][c][v] + m2 * w.at(v, 0)) - w0[v];
+                ctx.template store<2>(row, o);
             }
             B200_UNROLL
             for (int v = 0; v < V; v++) {
-                S.q[c][0][v] = S.q[c][1][v];
-                S.q[c][1][v] = S.q[c][2][v];
-                S.q[c][2][v] = S.q[c][3][v];
-                S.q[c][3][v] = w.at(v, 0);
-                S.pend[c][0][v] = S.pend[c][1][v];
-                S.pend[c][1][v] = pn[v];
+                const T cp = w.at(v, 0);
+                const T in1 = ((w.at(v, 1) + w.at(v, -1)) + u1[v]) + d1[v];
+                const T in2 = ((w.at(v, 2) + w.at(v, -2)) + u2[v]) + d2[v];
+                const T fresh = m0 * cp + m1 * (in1 + S.Cq[A1][c][v]) + m2 * (in2 + S.Cq[A0][c][v]);
+                S.acc[A1][c][v] += m1 * cp;
+                S.acc[A0][c][v] = fresh;
+                S.Cq[A0][c][v] = cp;
             }
         }
     }
@@ -118,24 +120,27 @@ template <typename T> struct Wave13ptOp {
 // ------------------------------------------------------------------------------------------
 // divergence: u = alpha*(ux[x+1]-ux[x-1]) + beta*(uy[y+1]-uy[y-1]) + gamma*(uz[z+1]-uz[z-1])
 //                                                                  divergence/divergence.c:93-96
+// ring z[2]: z[PH] = uz plane s-1, z[PH^1] = plane s; plane s+1 arrives.
+// u is rewritten every sweep and never read: streamed past the L2.
 // ------------------------------------------------------------------------------------------
 template <typename T> struct DivergenceOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 5, HOLD = 0, WARM = 2, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 5, HOLD = 0, WARM = 2, PERIOD = 2;
+    static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 3;
     static constexpr StagedSpec spec(int a)
     {
         return a == 0 ? StagedSpec{1, 1, 0, 0, 0, 0}     // ux: x halo, plane s
              : a == 1 ? StagedSpec{2, 0, 1, 1, 0, 0}     // uy: y halo, plane s
-                      : StagedSpec{3, 0, 0, 0, 1, 1};    // uz: planes s-1 .. s+1 through the queue
+                      : StagedSpec{3, 0, 0, 0, 1, 1};    // uz: planes s-1 .. s+1 through the ring
     }
     using G = Geo<DivergenceOp>;
     static constexpr int V = G::V, CPT = G::CPT;
-    struct State { T zm[CPT][V], z0[CPT][V]; };
+    struct State { T z[2][CPT][V]; };
     T alpha, beta, gamma;
     B200_DEV DivergenceOp(const StreamParams& P) : alpha((T)P.sc[0]), beta((T)P.sc[1]), gamma((T)P.sc[2]) {}
-    B200_DEV void pre(const Ctx<DivergenceOp>&, State&) {}
-    B200_DEV void step(const Ctx<DivergenceOp>& ctx, State& S)
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State& S)
     {
         constexpr int BW1 = G::bw(1);
         B200_UNROLL
@@ -151,14 +156,11 @@ template <typename T> struct DivergenceOp {
                 B200_UNROLL
                 for (int v = 0; v < V; v++)
                     o[v] = alpha * (wx.at(v, 1) - wx.at(v, -1)) + beta * (up[v] - dn[v]) +
-                           gamma * (zp[v] - S.zm[c][v]);
-                ctx.template store<0>(row, ctx.s, o);
+                           gamma * (zp[v] - S.z[PH][c][v]);
+                ctx.template store<0>(row, o);
             }
             B200_UNROLL
-            for (int v = 0; v < V; v++) {
-                S.zm[c][v] = S.z0[c][v];
-                S.z0[c][v] = zp[v];
-            }
+            for (int v = 0; v < V; v++) S.z[PH][c][v] = zp[v];
         }
     }
 };
@@ -166,47 +168,52 @@ template <typename T> struct DivergenceOp {
 // ------------------------------------------------------------------------------------------
 // gradient: ux = alpha*(u[x+1]-u[x-1]); uy = beta*(u[y+1]-u[y-1]); uz = gamma*(u[z+1]-u[z-1])
 //                                                                  gradient/gradient.c:95-97
+// When plane p = s+1 of u arrives, ux and uy OF PLANE p are stored at once (they only need that
+// plane) and uz of plane s = gamma*(C_p - C_{s-1}).  ring Cq[2]: Cq[PH&1] = C_{s-1}, Cq[(PH+1)&1] = C_s.
+// The three outputs are rewritten every sweep and never read: streamed past the L2.
 // ------------------------------------------------------------------------------------------
 template <typename T> struct GradientOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 8, HOLD = 0, WARM = 2, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 48 : 24), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
+    static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
     using G = Geo<GradientOp>;
     static constexpr int V = G::V, CPT = G::CPT;
-    struct State { T cm[CPT][V], c0[CPT][V], dx[CPT][V], dy[CPT][V]; };
+    struct State { T Cq[2][CPT][V]; };
     T alpha, beta, gamma;
     B200_DEV GradientOp(const StreamParams& P) : alpha((T)P.sc[0]), beta((T)P.sc[1]), gamma((T)P.sc[2]) {}
-    B200_DEV void pre(const Ctx<GradientOp>&, State&) {}
-    B200_DEV void step(const Ctx<GradientOp>& ctx, State& S)
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State& S)
     {
         constexpr int BW = G::bw(0);
+        constexpr int A0 = PH & 1;
+        const bool xy_plane = ctx.rel >= -1 && ctx.s + 1 < ctx.zb;      // plane s+1 is an output plane of this item
         B200_UNROLL
         for (int c = 0; c < CPT; c++) {
             const int row = ctx.ty + G::LY * c;
             const T* p = ctx.template tile<0>(row);          // u plane s+1
             Window<1, 1, T> w;
             w.load(p);
-            const VReg<T> up = ldv(p + BW), dn = ldv(p - BW);
-            if (ctx.rel >= 0) {
-                T ox[V], oy[V], oz[V];
+            if (xy_plane) {
+                const VReg<T> up = ldv(p + BW), dn = ldv(p - BW);
+                T ox[V], oy[V];
                 B200_UNROLL
                 for (int v = 0; v < V; v++) {
-                    ox[v] = alpha * S.dx[c][v];
-                    oy[v] = beta * S.dy[c][v];
-                    oz[v] = gamma * (w.at(v, 0) - S.cm[c][v]);
+                    ox[v] = alpha * (w.at(v, 1) - w.at(v, -1));
+                    oy[v] = beta * (up[v] - dn[v]);
                 }
-                ctx.template store<1>(row, ctx.s, ox);
-                ctx.template store<2>(row, ctx.s, oy);
-                ctx.template store<3>(row, ctx.s, oz);
+                ctx.template store<1>(row, ox, 1);
+                ctx.template store<2>(row, oy, 1);
+            }
+            if (ctx.rel >= 0) {
+                T oz[V];
+                B200_UNROLL
+                for (int v = 0; v < V; v++) oz[v] = gamma * (w.at(v, 0) - S.Cq[A0][c][v]);
+                ctx.template store<3>(row, oz);
             }
             B200_UNROLL
-            for (int v = 0; v < V; v++) {
-                S.cm[c][v] = S.c0[c][v];
-                S.c0[c][v] = w.at(v, 0);
-                S.dx[c][v] = w.at(v, 1) - w.at(v, -1);
-                S.dy[c][v] = up[v] - dn[v];
-            }
+            for (int v = 0; v < V; v++) S.Cq[A0][c][v] = w.at(v, 0);
         }
     }
 };
@@ -216,10 +223,12 @@ template <typename T> struct GradientOp {
 //       c2*(xx[i+1]-xx[i-2]) + c1*(xy[c]-xy[j-1]) + c2*(xy[j+1]-xy[j-2]) + c1*(xz[c]-xz[k-1]) +
 //       c2*(xz[k+1]-xz[k-2]) ),  dth = 1./nx                           uxx1/uxx1.c:70,95-105
 // The d sum keeps the reference's textual order (it is ill-conditioned); one IEEE division.
+// ring xq[3]: xq[(PH+k)%3] = xz plane s-2+k (k=0..2); plane s+1 arrives and replaces s-2.
 // ------------------------------------------------------------------------------------------
 template <typename T> struct Uxx1Op {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 12 : 6), STAGES = 5, HOLD = 0, WARM = 3, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 12 : 6), STAGES = 5, HOLD = 0, WARM = 3, PERIOD = 3;
+    static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 5;
     static constexpr StagedSpec spec(int a)
     {
@@ -227,17 +236,18 @@ template <typename T> struct Uxx1Op {
              : a == 1 ? StagedSpec{2, 0, 1, 0, 0, 1}     // d1: rows j-1..j, planes s-1..s
              : a == 2 ? StagedSpec{3, 1, 0, 0, 0, 0}     // xx: x-2..x+1, plane s
              : a == 3 ? StagedSpec{4, 0, 2, 1, 0, 0}     // xy: rows j-2..j+1, plane s
-                      : StagedSpec{5, 0, 0, 0, 1, 2};    // xz: planes s-2..s+1 through the queue
+                      : StagedSpec{5, 0, 0, 0, 1, 2};    // xz: planes s-2..s+1 through the ring
     }
     using G = Geo<Uxx1Op>;
     static constexpr int V = G::V, CPT = G::CPT;
-    struct State { T xq[CPT][3][V]; T dp[CPT][2][V]; };
+    struct State { T xq[3][CPT][V]; T dp[2][CPT][V]; };
     T c1, c2, dth;
     B200_DEV Uxx1Op(const StreamParams& P) : c1((T)P.sc[0]), c2((T)P.sc[1]), dth((T)(1. / P.nx)) {}
-    B200_DEV void pre(const Ctx<Uxx1Op>&, State&) {}
-    B200_DEV void step(const Ctx<Uxx1Op>& ctx, State& S)
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State& S)
     {
         constexpr int BWD = G::bw(1), BWY = G::bw(3);
+        constexpr int X0 = PH % 3, X1 = (PH + 1) % 3, X2 = (PH + 2) % 3;
         B200_UNROLL
         for (int c = 0; c < CPT; c++) {
             const int row = ctx.ty + G::LY * c;
@@ -257,22 +267,20 @@ template <typename T> struct Uxx1Op {
                 T o[V];
                 B200_UNROLL
                 for (int v = 0; v < V; v++) {
-                    const T d = (T)0.25 * (((dc[v] + dm[v]) + S.dp[c][0][v]) + S.dp[c][1][v]);
+                    const T d = (T)0.25 * (((dc[v] + dm[v]) + S.dp[0][c][v]) + S.dp[1][c][v]);
                     const T t = c1 * (wx.at(v, 0) - wx.at(v, -1)) + c2 * (wx.at(v, 1) - wx.at(v, -2)) +
                                 c1 * (y0[v] - ym1[v]) + c2 * (yp1[v] - ym2[v]) +
-                                c1 * (S.xq[c][2][v] - S.xq[c][1][v]) + c2 * (zp[v] - S.xq[c][0][v]);
+                                c1 * (S.xq[X2][c][v] - S.xq[X1][c][v]) + c2 * (zp[v] - S.xq[X0][c][v]);
                     o[v] = u0[v] + (dth / d) * t;
                 }
-                ctx.template store<1>(row, ctx.s, o);
+                ctx.template store<1>(row, o);
             }
             B200_UNROLL
             for (int v = 0; v < V; v++) {
-                S.xq[c][0][v] = S.xq[c][1][v];
-                S.xq[c][1][v] = S.xq[c][2][v];
-                S.xq[c][2][v] = zp[v];
+                S.xq[X0][c][v] = zp[v];
                 if (ctx.rel >= -1) {
-                    S.dp[c][0][v] = dc[v];
-                    S.dp[c][1][v] = dm[v];
+                    S.dp[0][c][v] = dc[v];
+                    S.dp[1][c][v] = dm[v];
                 }
             }
         }
@@ -281,26 +289,30 @@ template <typename T> struct Uxx1Op {
 
 // ------------------------------------------------------------------------------------------
 // lapgsrb: w1 = c0*w0 + c1*(6 faces) + c2*(12 edge diagonals) + c3*(6 radius-2)   lapgsrb/lapgsrb.c:93-117
-// z-scatter form: when plane p arrives its in-plane sums are formed once:
-//   C_p centre, F_p = x+-1 + y+-1, D_p = 4 in-plane diagonals, G_p = x+-2 + y+-2,
-//   A_p = c0*C_p + c1*F_p + c2*D_p + c3*G_p
-// and  out_s = A_s + c1*(C_{s+1}+C_{s-1}) + c2*(F_{s+1}+F_{s-1}) + c3*(C_{s+2}+C_{s-2})
-// (the edge diagonals in planes s+-1 are exactly F of those planes).  Re-associated.
+// Accumulate-forward z-scatter form.  For an arriving plane p = s+2 the in-plane sums are formed
+// once: C_p centre, F_p = x+-1 + y+-1, D_p = 4 in-plane diagonals, G_p = x+-2 + y+-2 (the edge
+// diagonals that live in planes k+-1 of an output k are exactly F of those planes), then
+//     out_s      = acc_s + c3*C_p                                           (emitted)
+//     acc_{s+1} += c1*C_p + c2*F_p
+//     acc_p      = c0*C_p + c1*F_p + c2*D_p + c3*G_p + c1*C_{p-1} + c2*F_{p-1} + c3*C_{p-2}
+// Five live values per point: rings of two for acc and C, one F.  Re-associated.
 // ------------------------------------------------------------------------------------------
 template <typename T> struct LapgsrbOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 8, HOLD = 0, WARM = 4, MIN_BLOCKS = 1;
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 8, HOLD = 0, WARM = 4, PERIOD = 2;
+    static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 2, 2, 2, 2}; }
     using G = Geo<LapgsrbOp>;
     static constexpr int V = G::V, CPT = G::CPT;
-    struct State { T C[CPT][4][V]; T F[CPT][3][V]; T A[CPT][2][V]; };
+    struct State { T acc[2][CPT][V]; T Cq[2][CPT][V]; T Fp[CPT][V]; };
     T c0, c1, c2, c3;
     B200_DEV LapgsrbOp(const StreamParams& P) : c0((T)P.sc[0]), c1((T)P.sc[1]), c2((T)P.sc[2]), c3((T)P.sc[3]) {}
-    B200_DEV void pre(const Ctx<LapgsrbOp>&, State&) {}
-    B200_DEV void step(const Ctx<LapgsrbOp>& ctx, State& S)
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State& S)
     {
         constexpr int BW = G::bw(0);
+        constexpr int A0 = PH & 1, A1 = (PH + 1) & 1;
         B200_UNROLL
         for (int c = 0; c < CPT; c++) {
             const int row = ctx.ty + G::LY * c;
@@ -311,33 +323,23 @@ template <typename T> struct LapgsrbOp {
             wu.load(p + BW);
             wd.load(p - BW);
             const VReg<T> u2 = ldv(p + 2 * BW), d2 = ldv(p - 2 * BW);
-            T Fn[V], An[V];
-            B200_UNROLL
-            for (int v = 0; v < V; v++) {
-                Fn[v] = ((w.at(v, 1) + w.at(v, -1)) + wu.at(v, 0)) + wd.at(v, 0);
-                const T Dn = ((wu.at(v, 1) + wd.at(v, 1)) + wu.at(v, -1)) + wd.at(v, -1);
-                const T Gn = ((w.at(v, 2) + w.at(v, -2)) + u2[v]) + d2[v];
-                An[v] = c0 * w.at(v, 0) + c1 * Fn[v] + c2 * Dn + c3 * Gn;
-            }
             if (ctx.rel >= 0) {
                 T o[V];
                 B200_UNROLL
-                for (int v = 0; v < V; v++)
-                    o[v] = S.A[c][0][v] + c1 * (S.C[c][3][v] + S.C[c][1][v]) +
-                           c2 * (S.F[c][2][v] + S.F[c][0][v]) + c3 * (w.at(v, 0) + S.C[c][0][v]);
-                ctx.template store<1>(row, ctx.s, o);
+                for (int v = 0; v < V; v++) o[v] = S.acc[A0][c][v] + c3 * w.at(v, 0);
+                ctx.template store<1>(row, o);
             }
             B200_UNROLL
             for (int v = 0; v < V; v++) {
-                S.C[c][0][v] = S.C[c][1][v];
-                S.C[c][1][v] = S.C[c][2][v];
-                S.C[c][2][v] = S.C[c][3][v];
-                S.C[c][3][v] = w.at(v, 0);
-                S.F[c][0][v] = S.F[c][1][v];
-                S.F[c][1][v] = S.F[c][2][v];
-                S.F[c][2][v] = Fn[v];
-                S.A[c][0][v] = S.A[c][1][v];
-                S.A[c][1][v] = An[v];
+                const T cp = w.at(v, 0);
+                const T Fn = ((w.at(v, 1) + w.at(v, -1)) + wu.at(v, 0)) + wd.at(v, 0);
+                const T Dn = ((wu.at(v, 1) + wd.at(v, 1)) + wu.at(v, -1)) + wd.at(v, -1);
+                const T Gn = ((w.at(v, 2) + w.at(v, -2)) + u2[v]) + d2[v];
+                const T fresh = c0 * cp + c1 * (Fn + S.Cq[A1][c][v]) + c2 * (Dn + S.Fp[c][v]) + c3 * (Gn + S.Cq[A0][c][v]);
+                S.acc[A1][c][v] += c1 * cp + c2 * Fn;
+                S.acc[A0][c][v] = fresh;
+                S.Cq[A0][c][v] = cp;
+                S.Fp[c][v] = Fn;
             }
         }
     }
@@ -348,7 +350,8 @@ template <typename T> struct LapgsrbOp {
 //                          tricubic/tricubic.c:1027-1145 ; tricubic2/tricubic2.c:81-102
 // Evaluated separably (x, then y, then z): 84 FMA + weights instead of the reference's 64
 // three-factor products -- a re-association.  The four u0 planes s-1..s+2 stay in the ring
-// (HOLD = 3); a,b,c are point-wise and come straight from global memory with 16-byte loads.
+// (HOLD = 3); a,b,c are point-wise planes staged by TMA in the same ring (direct global loads
+// exposed a DRAM latency per step: measured 8 stall cycles per issue on long scoreboard).
 // tricubic and tricubic2 differ only in the interior bounds (b200_test_info).
 // ------------------------------------------------------------------------------------------
 template <typename T> B200_DEV void cubic_weights(T t, T (&w)[4])
@@ -363,53 +366,35 @@ template <typename T> B200_DEV void cubic_weights(T t, T (&w)[4])
 
 template <typename T> struct TricubicOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 8, HOLD = 3, WARM = 3, MIN_BLOCKS = 1;
-    static constexpr int NSTAGED = 1;
-    static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 2, 2, 1}; }
+    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 12 : 6), STAGES = 6, HOLD = 3, WARM = 3, PERIOD = 1;
+    static constexpr bool STREAM_OUT = false;
+    static constexpr int NSTAGED = 4;
+    static constexpr StagedSpec spec(int a)
+    {
+        return a == 0 ? StagedSpec{0, 1, 1, 2, 2, 1}      // u0: x -1..+2, y -1..+2, planes s-1..s+2 (held in the ring)
+                      : StagedSpec{a + 1, 0, 0, 0, 0, 0}; // a, b, c (slots 2,3,4): point-wise, plane s
+    }
     using G = Geo<TricubicOp>;
     static constexpr int V = G::V, CPT = G::CPT;
-    struct State { T a[CPT][V], b[CPT][V], c[CPT][V]; };
+    struct State { };
     B200_DEV TricubicOp(const StreamParams&) {}
-
-    template <int SLOT> B200_DEV static void gload(const Ctx<TricubicOp>& ctx, int row, T (&out)[V])
-    {
-        const T* p = ctx.template gptr<SLOT>(row, ctx.s);
-        if (ctx.vec_in_array(row)) {
-            const VReg<T> r = ldv_stream(p);
-            B200_UNROLL
-            for (int v = 0; v < V; v++) out[v] = r[v];
-        } else {
-            const bool yin = (ctx.Y0 + row) >= 0 && (ctx.Y0 + row) < ctx.P.ny;
-            B200_UNROLL
-            for (int v = 0; v < V; v++) out[v] = (yin && ctx.gx() + v < ctx.P.nx) ? p[v] : (T)0;
-        }
-    }
-    // a,b,c loads are issued before the wait on the stage so their latency overlaps it
-    B200_DEV void pre(const Ctx<TricubicOp>& ctx, State& S)
-    {
-        if (ctx.rel < 0) return;
-        B200_UNROLL
-        for (int c = 0; c < CPT; c++) {
-            const int row = ctx.ty + G::LY * c;
-            gload<2>(ctx, row, S.a[c]);
-            gload<3>(ctx, row, S.b[c]);
-            gload<4>(ctx, row, S.c[c]);
-        }
-    }
-    B200_DEV void step(const Ctx<TricubicOp>& ctx, State& S)
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State&)
     {
         if (ctx.rel < 0) return;
         constexpr int BW = G::bw(0);
         B200_UNROLL
         for (int c = 0; c < CPT; c++) {
             const int row = ctx.ty + G::LY * c;
+            const VReg<T> va = ldv(ctx.template tile<1>(row)), vb = ldv(ctx.template tile<2>(row)),
+                          vc = ldv(ctx.template tile<3>(row));
             T o[V];
             T wa[V][4], wb[V][4], wc[V][4];
             B200_UNROLL
             for (int v = 0; v < V; v++) {
-                cubic_weights(S.a[c][v], wa[v]);
-                cubic_weights(S.b[c][v], wb[v]);
-                cubic_weights(S.c[c][v], wc[v]);
+                cubic_weights(va[v], wa[v]);
+                cubic_weights(vb[v], wb[v]);
+                cubic_weights(vc[v], wc[v]);
                 o[v] = (T)0;
             }
             B200_UNROLL
@@ -432,7 +417,7 @@ template <typename T> struct TricubicOp {
                 B200_UNROLL
                 for (int v = 0; v < V; v++) o[v] += wc[v][kk] * pz[v];
             }
-            ctx.template store<1>(row, ctx.s, o);
+            ctx.template store<1>(row, o);
         }
     }
 };

@@ -59,7 +59,6 @@ struct StreamParams {
     void* push_hi; int push_hi_src, push_hi_dst, push_hi_cnt;
     int push_slot;
     int push_dim;                   // 2: planes (3D tests), 1: rows (2D tests)
-    int store_cs;                   // 1: streaming (evict-first) stores
     int reverse;                    // 1: walk the items in reverse order (serpentine sweeps)
 };
 
@@ -96,32 +95,39 @@ template <class Op> struct Geo {
     static_assert(Op::STAGES > Op::HOLD, "ring too shallow");
 };
 
-// What Op::step() sees.  Everything that is invariant over an item (tile) or a step is computed
-// once there, so a store costs a row test, one multiply-add and the address add.
-template <class Op> struct Ctx {
+// What Op::step() sees.  Everything invariant over an item (tile) or a step is computed once
+// there: a store is a row test, one multiply-add for the 32-bit element offset and one 64-bit
+// address add off a warp-uniform plane pointer.  PUSH = this launch also stores halo planes into
+// a neighbour GPU's memory; single-GPU launches are compiled without that code.
+template <class Op, bool PUSH> struct Ctx {
     using T = typename Op::real;
     using G = Geo<Op>;
+    static constexpr int V = G::V;
     const StreamParams& P;
     unsigned char* stages;      // base of the ring
     uint32_t st;                // ring stage of this step
     int X0, Y0;                 // global x of tile column 0, global y of tile row 0
     int s;                      // output plane of this step
     int rel;                    // s - (first output plane of the item); < 0 during warm-up
+    int zb;                     // per item: end of the item's output planes
     int tx, ty;                 // consumer thread coordinates
-    int x;                      // global x of this thread's vector (per item)
+    int x;                      // per item: global x of this thread's vector
     int xmode;                  // per item: 1 = whole vector inside [xlo,xhi) and 16-byte stores legal,
                                 //           2 = some elements inside, 0 = none
-    unsigned yspan;             // yhi - ylo
+    int rows_valid;             // per item: tile rows [0, rows_valid) are inside [ylo, yhi)
+    unsigned idx0;              // per item: Y0 * nx + x  (element index of tile row 0 within a plane)
+    long long poff;             // per step: s * nx * ny  (element offset of the output plane; warp-uniform)
 
     B200_DEV void begin_item(int X0_, int Y0_)
     {
         X0 = X0_;
         Y0 = Y0_;
-        x = X0 + G::V * tx;
-        const bool some = x + G::V > P.xlo && x < P.xhi;
-        const bool all = x >= P.xlo && x + G::V <= P.xhi;
+        x = X0 + V * tx;
+        const bool some = x + V > P.xlo && x < P.xhi;
+        const bool all = x >= P.xlo && x + V <= P.xhi;
         xmode = (all && P.vec_ok) ? 1 : (some ? 2 : 0);
-        yspan = (unsigned)(P.yhi - P.ylo);
+        rows_valid = min(G::TY, P.yhi - Y0);
+        idx0 = (unsigned)(Y0 * P.nx + x);
     }
 
     // Pointer to this thread's 16-byte vector in tile row `row` (tile-local output row, may be
@@ -131,60 +137,77 @@ template <class Op> struct Ctx {
         uint32_t q = st;
         if (back) q = (st + (uint32_t)Op::STAGES - (uint32_t)back) % (uint32_t)Op::STAGES;
         const T* base = reinterpret_cast<const T*>(stages + q * G::STAGE_BYTES + G::arr_off(A));
-        return base + (row + Op::spec(A).ylo) * G::bw(A) + G::hxp(A) + G::V * tx;
+        return base + (row + Op::spec(A).ylo) * G::bw(A) + G::hxp(A) + V * tx;
     }
     B200_DEV int gx() const { return x; }
 
-    // Read-only pointer into a global array at (x of this thread, tile row, plane).
-    template <int SLOT> B200_DEV const T* gptr(int row, int plane) const
+    // Read-only pointer into a global array at (x of this thread, tile row, plane s).
+    template <int SLOT> B200_DEV const T* gptr(int row) const
     {
-        const T* a = reinterpret_cast<const T*>(P.arr[SLOT]);
-        return a + ((size_t)plane * P.ny + (size_t)(Y0 + row)) * P.nx + x;
+        return reinterpret_cast<const T*>(P.arr[SLOT]) + poff + (idx0 + (unsigned)(row * P.nx));
     }
     // true when this thread's whole 16-byte vector at (row, any plane) is inside the array
     B200_DEV bool vec_in_array(int row) const
     {
-        return P.vec_ok && x + G::V <= P.nx && (Y0 + row) >= 0 && (Y0 + row) < P.ny;
+        return P.vec_ok && x + V <= P.nx && (Y0 + row) >= 0 && (Y0 + row) < P.ny;
     }
 
-    // 16-byte (or element-predicated) store of V values at (x of this thread, y, plane) of array a
-    B200_DEV void store_vec(T* a, int y, int plane, const T (&val)[G::V]) const
+    // 16-byte (or element-predicated) store of V values
+    B200_DEV void put(T* dst, const T (&val)[V]) const
     {
-        T* dst = a + ((size_t)plane * P.nxny + (size_t)(y * P.nx + x));
         if (xmode == 1) {
             VReg<T> r;
 #pragma unroll
-            for (int v = 0; v < G::V; v++) r[v] = val[v];
-            if (P.store_cs) __stcs(reinterpret_cast<uint4*>(dst), *reinterpret_cast<const uint4*>(r.v));
+            for (int v = 0; v < V; v++) r[v] = val[v];
+            if constexpr (Op::STREAM_OUT) __stcs(reinterpret_cast<uint4*>(dst), *reinterpret_cast<const uint4*>(r.v));
             else *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(r.v);
         } else {
 #pragma unroll
-            for (int v = 0; v < G::V; v++)
+            for (int v = 0; v < V; v++)
                 if (x + v >= P.xlo && x + v < P.xhi) dst[v] = val[v];
         }
     }
 
-    // Store V results of output array SLOT at (tile row, plane); interior-predicated.
-    template <int SLOT> B200_DEV void store(int row, int plane, const T (&val)[G::V]) const
+    // Store V results of output array SLOT at tile row `row` of the step's output plane (plane s
+    // for the 3D tests, the only plane for the 2D tests); interior-predicated.
+    // dplane: store into plane s + dplane instead (no halo push for those).
+    template <int SLOT> B200_DEV void store(int row, const T (&val)[V], int dplane = 0) const
     {
-        const int y = Y0 + row;
-        if ((unsigned)(y - P.ylo) >= yspan || xmode == 0) return;
-        store_vec(reinterpret_cast<T*>(P.arr[SLOT]), y, plane, val);
-        if (SLOT == P.push_slot) {
+        if (row >= rows_valid || xmode == 0) return;
+        const unsigned off = idx0 + (unsigned)(row * P.nx);
+        put(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val);
+        if constexpr (PUSH) {
             // fused halo push: the same values also go to the neighbour GPU's ghost planes (rows for
             // the 2D tests) through a peer-mapped pointer, i.e. over NVLink, while the sweep runs
-            const int coord = P.push_dim == 2 ? plane : y;
-            if (P.push_lo && coord >= P.push_lo_src && coord < P.push_lo_src + P.push_lo_cnt) {
-                const int d = coord - P.push_lo_src + P.push_lo_dst;
-                store_vec(reinterpret_cast<T*>(P.push_lo), P.push_dim == 2 ? y : d, P.push_dim == 2 ? d : plane, val);
-            }
-            if (P.push_hi && coord >= P.push_hi_src && coord < P.push_hi_src + P.push_hi_cnt) {
-                const int d = coord - P.push_hi_src + P.push_hi_dst;
-                store_vec(reinterpret_cast<T*>(P.push_hi), P.push_dim == 2 ? y : d, P.push_dim == 2 ? d : plane, val);
+            if (SLOT == P.push_slot) {
+                const int coord = P.push_dim == 2 ? s : Y0 + row;
+                if (P.push_lo && coord >= P.push_lo_src && coord < P.push_lo_src + P.push_lo_cnt) {
+                    const long long d = coord - P.push_lo_src + P.push_lo_dst;
+                    T* base = reinterpret_cast<T*>(P.push_lo);
+                    put(P.push_dim == 2 ? base + d * P.nxny + off : base + d * P.nx + x, val);
+                }
+                if (P.push_hi && coord >= P.push_hi_src && coord < P.push_hi_src + P.push_hi_cnt) {
+                    const long long d = coord - P.push_hi_src + P.push_hi_dst;
+                    T* base = reinterpret_cast<T*>(P.push_hi);
+                    put(P.push_dim == 2 ? base + d * P.nxny + off : base + d * P.nx + x, val);
+                }
             }
         }
     }
 };
+
+// Ops keep their z queues in register rings indexed by a compile-time phase (no shifting moves):
+// the step loop dispatches on phase = step-in-item mod Op::PERIOD.
+template <class Op, class C, int PH = 0>
+B200_DEV void step_dispatch(Op& op, const C& ctx, typename Op::State& state, int phase)
+{
+    if constexpr (PH + 1 >= Op::PERIOD) {
+        op.template step<PH>(ctx, state);
+    } else {
+        if (phase == PH) op.template step<PH>(ctx, state);
+        else step_dispatch<Op, C, PH + 1>(op, ctx, state, phase);
+    }
+}
 
 // Producer-side fallback: fill one staged box with bounds-checked scalar loads (zero fill outside).
 template <class Op, int A>
@@ -260,7 +283,7 @@ template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int i
 // (measured: profiles/README.md).
 template <class Op> struct RegCap { static constexpr int value = 128; };
 
-template <class Op>
+template <class Op, bool PUSH>
 __global__ void __launch_bounds__(NTHREADS) __maxnreg__(RegCap<Op>::value)
 stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ TensorMaps M)
 {
@@ -316,26 +339,29 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
         // ------------------------------ consumer warps ------------------------------
         Op op(P);
         typename Op::State state;
-        Ctx<Op> ctx{P, stages, 0u, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0u};
-        uint32_t st = 0, ph = 0, rel_st = (uint32_t)(S - Op::HOLD) % S;    // ring stage / phase of this step; stage to hand back
+        Ctx<Op, PUSH> ctx{P, stages, 0u, 0, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0, 0u, 0ll};
+        uint32_t st = 0, ph = 0, rel_st = (uint32_t)(S - Op::HOLD) % S;    // ring stage / parity of this step; stage to hand back
         uint32_t g = 0;
         for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
             const ItemCoords c = decode_item<Op>(P, item);
             ctx.begin_item(c.X0, c.Y0);
-            int local = 0;
+            ctx.zb = c.zb;
+            int local = 0, phase = 0;
             for (int s = c.za - Op::WARM; s < c.zb; ++s, ++g, ++local) {
                 ctx.st = st;
                 ctx.s = s;
                 ctx.rel = s - c.za;
+                ctx.poff = (long long)s * P.nxny;
                 op.pre(ctx, state);
                 mbar_wait(&full[st], ph);
-                op.step(ctx, state);
+                step_dispatch<Op, Ctx<Op, PUSH>>(op, ctx, state, phase);
                 if (local >= Op::HOLD) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[rel_st]);
                 }
                 if (++st == S) { st = 0; ph ^= 1u; }
                 if (++rel_st == S) rel_st = 0;
+                if (++phase == Op::PERIOD) phase = 0;
             }
             if constexpr (Op::HOLD > 0) {
                 // hand back the stages still held at the end of the item
