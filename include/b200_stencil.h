@@ -116,6 +116,14 @@ typedef struct {
     /* 1: walk the work items back to front.  Alternating 0/1 between consecutive sweeps makes a
      * sweep start on the data its predecessor touched last, which is still in L2. */
     int reverse_order;
+    /* Ordering between neighbour ranks, done INSIDE the sweep kernel (only with push_lo/push_hi):
+     * before touching any data the kernel spins until *wait_flag[i] >= wait_value (acquire, system
+     * scope; NULL = no wait), and when the last CTA has finished it stores signal_value to
+     * signal_flag[i] (release, system scope; normally a flag in the neighbour's memory). */
+    const void* wait_flag[2];
+    unsigned long long wait_value;
+    void* signal_flag[2];
+    unsigned long long signal_value;
 } b200_sweep_desc;
 
 /* One sweep: arrays[] are DEVICE pointers in slot order (current rotation
@@ -128,6 +136,16 @@ int b200_sweep(const b200_sweep_desc* desc, void* const* arrays, void* stream);
  * the order the next sweep would see them.  Not for sweeps that push halos (those need the
  * per-sweep b200_wait / b200_signal ordering). */
 int b200_sweep_loop(const b200_sweep_desc* desc, void** arrays, int niters, void* stream);
+
+/* The nt-loop of one z-slab whose neighbours are other processes / GPUs: `niters` sweeps back to
+ * back, each pushing its boundary planes into the neighbours' copy of the array it writes
+ * (peer_lo[] / peer_hi[]: the neighbours' buffers in the SAME rotation order as arrays[], peer
+ * mapped; NULL entries = no neighbour on that side) and ordered against the neighbours purely on
+ * the device: sweep number n (counted from first_sweep) waits for flag value n on
+ * desc->wait_flag[] and publishes n+1 on desc->signal_flag[].  desc carries the plane ranges
+ * (push_*_src_plane / dst_plane / count).  arrays[], peer_lo[], peer_hi[] are rotated in place. */
+int b200_slab_loop(const b200_sweep_desc* desc, void** arrays, void** peer_lo, void** peer_hi,
+                   int niters, unsigned long long first_sweep, void* stream);
 
 /* Registers per thread / kernel symbol of the kernel b200_sweep would launch. */
 int b200_kernel_info(int test, int dtype, int* regs_per_thread, const char** kernel_name);

@@ -26,7 +26,7 @@ MAX_ARRAYS, MAX_SCALARS = 8, 8
 
 # every symbol include/b200_stencil.h declares (checked by tests/test_abi.py)
 EXPORTS = ["b200_get_test_info", "b200_test_by_name", "b200_last_error", "b200_api_version",
-           "b200_interior_points", "b200_device_count", "b200_sweep", "b200_sweep_loop", "b200_kernel_info",
+           "b200_interior_points", "b200_device_count", "b200_sweep", "b200_sweep_loop", "b200_slab_loop", "b200_kernel_info",
            "b200_launch_count", "b200_init", "b200_plan", "b200_alloc", "b200_load", "b200_run",
            "b200_result_slot", "b200_save", "b200_free", "b200_destroy", "b200_host_alloc",
            "b200_host_free", "b200_device_alloc", "b200_device_free", "b200_ipc_export",
@@ -51,7 +51,9 @@ class SweepDesc(C.Structure):
                 ("push_lo", C.c_void_p), ("push_lo_src_plane", C.c_int), ("push_lo_dst_plane", C.c_int),
                 ("push_lo_count", C.c_int),
                 ("push_hi", C.c_void_p), ("push_hi_src_plane", C.c_int), ("push_hi_dst_plane", C.c_int),
-                ("push_hi_count", C.c_int), ("reverse_order", C.c_int)]
+                ("push_hi_count", C.c_int), ("reverse_order", C.c_int),
+                ("wait_flag", C.c_void_p * 2), ("wait_value", C.c_ulonglong),
+                ("signal_flag", C.c_void_p * 2), ("signal_value", C.c_ulonglong)]
 
 
 class Stats(C.Structure):
@@ -83,6 +85,8 @@ def load() -> C.CDLL:
     L.b200_device_count.argtypes = [C.POINTER(C.c_int)]
     L.b200_sweep.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.c_void_p]
     L.b200_sweep_loop.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    L.b200_slab_loop.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                 C.c_int, C.c_ulonglong, C.c_void_p]
     L.b200_kernel_info.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_char_p)]
     L.b200_launch_count.restype = C.c_ulonglong
     L.b200_init.argtypes = [C.POINTER(C.c_void_p), C.c_int]
@@ -174,6 +178,28 @@ def sweep_loop(test, dtype, nx, ny, ns, scalars, device_ptrs, niters, stream=0, 
     ptrs = (C.c_void_p * len(device_ptrs))(*device_ptrs)
     _check(load().b200_sweep_loop(C.byref(d), ptrs, niters, C.c_void_p(stream)))
     return [int(p) if p else 0 for p in ptrs]
+
+
+def slab_loop(test, dtype, nx, ny, ns, scalars, device_ptrs, peer_lo, peer_hi, niters, first_sweep,
+              out_range, push_lo, push_hi, wait_flags, signal_flags, stream=0):
+    """`niters` sweeps of one slab with fused halo push and in-kernel neighbour ordering (b200_slab_loop).
+    peer_lo / peer_hi: the neighbours' buffers in rotation order (0 = none); push_lo / push_hi =
+    (src_plane, dst_plane, count); wait_flags / signal_flags: two addresses each (0 = none)."""
+    d = SweepDesc()
+    d.test, d.dtype, d.nx, d.ny, d.ns = _tid(test), _DT[dtype], nx, ny, ns
+    for i, v in enumerate(scalars):
+        d.scalars[i] = float(v)
+    d.out_begin, d.out_end = out_range
+    d.push_lo_src_plane, d.push_lo_dst_plane, d.push_lo_count = push_lo
+    d.push_hi_src_plane, d.push_hi_dst_plane, d.push_hi_count = push_hi
+    for i in range(2):
+        d.wait_flag[i] = wait_flags[i] or None
+        d.signal_flag[i] = signal_flags[i] or None
+    n = len(device_ptrs)
+    arr = (C.c_void_p * n)(*device_ptrs)
+    plo = (C.c_void_p * n)(*[p or None for p in peer_lo])
+    phi = (C.c_void_p * n)(*[p or None for p in peer_hi])
+    _check(load().b200_slab_loop(C.byref(d), arr, plo, phi, niters, first_sweep, C.c_void_p(stream)))
 
 
 def device_alloc(nbytes: int) -> int:

@@ -149,6 +149,19 @@ int get_tensor_map(const TmaBoxKey& key, void* out_map)
     return B200_OK;
 }
 
+static unsigned int* g_done_counter[16] = {};
+int get_done_counter(int device, unsigned int** counter)
+{
+    std::lock_guard<std::mutex> lk(g_tma_mu);
+    if (device < 0 || device >= 16) { set_error("device index %d out of range", device); return B200_ERR_ARG; }
+    if (!g_done_counter[device]) {
+        B200_CUDA(cudaMalloc(&g_done_counter[device], 256));
+        B200_CUDA(cudaMemset(g_done_counter[device], 0, 256));
+    }
+    *counter = g_done_counter[device];
+    return B200_OK;
+}
+
 static void drop_tensor_maps_for(const void* lo, const void* hi)
 {
     std::lock_guard<std::mutex> lk(g_tma_mu);
@@ -251,6 +264,40 @@ int b200_sweep_loop(const b200_sweep_desc* desc, void** arrays, int niters, void
         // the reference driver's rotation: laplacian.c:299-300 (swap), wave13pt.c:919-920 (3-cycle)
         if (ti->rotation == 2) { void* w = arrays[0]; arrays[0] = arrays[1]; arrays[1] = w; }
         else if (ti->rotation == 3) { void* w = arrays[0]; arrays[0] = arrays[1]; arrays[1] = arrays[2]; arrays[2] = w; }
+    }
+    return B200_OK;
+}
+
+int b200_slab_loop(const b200_sweep_desc* desc, void** arrays, void** peer_lo, void** peer_hi,
+                   int niters, unsigned long long first_sweep, void* stream)
+{
+    if (int rc = check_sweep_args(desc, arrays)) return rc;
+    if (niters < 0 || !peer_lo || !peer_hi) { set_error("b200_slab_loop: bad arguments"); return B200_ERR_ARG; }
+    const b200_test_info* ti = &g_tests[desc->test];
+    if (ti->exchange_slot < 0 || !ti->rotation) { set_error("%s has no exchanged array", ti->name); return B200_ERR_ARG; }
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    DeviceInfo di;
+    if (int rc = probe_device(dev, &di)) return rc;
+    b200_sweep_desc d = *desc;
+    HostArgs a{&d, arrays, (cudaStream_t)stream, dev, di.num_sms};
+    const int rot = ti->rotation, out_pos = rot == 3 ? 2 : 1;
+    for (int it = 0; it < niters; it++) {
+        const unsigned long long n = first_sweep + (unsigned long long)it;
+        d.reverse_order = (int)(n & 1ull);
+        d.push_lo = peer_lo[out_pos];
+        d.push_hi = peer_hi[out_pos];
+        d.wait_value = n;                         // flags start at 0: sweep 0 does not wait
+        d.signal_value = n + 1;
+        if (!d.push_lo) { d.push_lo_count = 0; }
+        if (!d.push_hi) { d.push_hi_count = 0; }
+        if (!d.push_lo && !d.push_hi) { set_error("b200_slab_loop: no neighbour"); return B200_ERR_ARG; }
+        if (int rc = g_launch[desc->test](desc->dtype, a)) return rc;
+        void** sets[3] = { arrays, peer_lo, peer_hi };
+        for (void** w : sets) {
+            if (rot == 2) { void* t = w[0]; w[0] = w[1]; w[1] = t; }
+            else { void* t = w[0]; w[0] = w[1]; w[1] = w[2]; w[2] = t; }
+        }
     }
     return B200_OK;
 }
@@ -498,6 +545,12 @@ int b200_alloc(b200_ctx* c)
         B200_CUDA(cudaEventCreateWithFlags(&s.done[1], cudaEventDisableTiming));
         B200_CUDA(cudaEventCreate(&s.t0));
         B200_CUDA(cudaEventCreate(&s.t1));
+        // one-time per-device kernel setup (module load, shared-memory attribute, occupancy) belongs
+        // to the allocation phase, not to the first timed sweep
+        KernelInfo ki{};
+        if (int rc = g_info[c->test](c->dtype, &ki)) return rc;
+        unsigned int* dc = nullptr;
+        if (c->ngpus > 1) { if (int rc = get_done_counter(s.dev, &dc)) return rc; }
     }
     B200_CUDA(cudaSetDevice(c->slab[0].dev));
     c->allocated = true;

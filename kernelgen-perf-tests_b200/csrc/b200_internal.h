@@ -60,4 +60,7 @@ struct TmaBoxKey {
 };
 int get_tensor_map(const TmaBoxKey& key, void* out_map /* CUtensorMap* */);
 
+// Per-device CTA completion counter used by PUSH launches to elect the signalling CTA.
+int get_done_counter(int device, unsigned int** counter);
+
 }  // namespace b200

@@ -124,6 +124,13 @@ template <class Op> int launch_stream(const HostArgs& a)
         P.push_lo = d.push_lo; P.push_lo_src = d.push_lo_src_plane; P.push_lo_dst = d.push_lo_dst_plane; P.push_lo_cnt = d.push_lo_count;
         P.push_hi = d.push_hi; P.push_hi_src = d.push_hi_src_plane; P.push_hi_dst = d.push_hi_dst_plane; P.push_hi_cnt = d.push_hi_count;
         if (((uintptr_t)d.push_lo) % 16 || ((uintptr_t)d.push_hi) % 16) P.vec_ok = 0;
+        for (int i = 0; i < 2; i++) {
+            P.wait_flag[i] = (const unsigned long long*)d.wait_flag[i];
+            P.signal_flag[i] = (unsigned long long*)d.signal_flag[i];
+        }
+        P.wait_value = d.wait_value;
+        P.signal_value = d.signal_value;
+        if (int rc = get_done_counter(a.device, &P.done_counter)) return rc;
     }
 
     P.ntx = (P.nx + Op::TX - 1) / Op::TX;
@@ -160,6 +167,8 @@ template <class Op> int info_stream(KernelInfo* ki, const char* name)
     B200_CUDA(cudaGetDevice(&dev));
     if (int rc = kernel_setup<Op, false>().get(dev, &bps)) return rc;
     ki->blocks_per_sm = bps;
+    int bps_push = 0;      // also prepares the halo-pushing variant (used by multi-GPU launches)
+    if (int rc = kernel_setup<Op, true>().get(dev, &bps_push)) return rc;
     return B200_OK;
 }
 

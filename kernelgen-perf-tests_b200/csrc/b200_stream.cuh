@@ -59,6 +59,13 @@ struct StreamParams {
     void* push_hi; int push_hi_src, push_hi_dst, push_hi_cnt;
     int push_slot;
     int push_dim;                   // 2: planes (3D tests), 1: rows (2D tests)
+    // in-kernel ordering between neighbour ranks (PUSH launches): before the sweep spin until
+    // *wait_flag[i] >= wait_value; after it the last CTA to finish stores signal_value to signal_flag[i]
+    const unsigned long long* wait_flag[2];
+    unsigned long long wait_value;
+    unsigned long long* signal_flag[2];
+    unsigned long long signal_value;
+    unsigned int* done_counter;     // per-device CTA completion counter (library-owned, self-resetting)
     int reverse;                    // 1: walk the items in reverse order (serpentine sweeps)
 };
 
@@ -305,13 +312,31 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
             mbar_init(&empty[i], NCONS / 32);
         }
         mbar_fence_init();
+        if constexpr (PUSH) {
+            // the neighbours' previous sweep must have finished pushing our ghosts (and reading theirs)
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const unsigned long long* f = P.wait_flag[i];
+                if (f) {
+                    unsigned long long cur, t0, now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                    for (;;) {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(f) : "memory");
+                        if (cur >= P.wait_value) break;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (now - t0 > 20000000000ull) __trap();      // a neighbour died: fail, do not hang
+                        __nanosleep(100);
+                    }
+                }
+            }
+        }
     }
     __syncthreads();
 
     if (warp == NCONS / 32) {
         // ------------------------------ producer warp ------------------------------
         if (P.use_tma) {
-            if (lane != 0) return;
+            if (lane != 0) goto finish;
 #pragma unroll
             for (int a = 0; a < Op::NSTAGED; a++) tma_prefetch_desc(&M.m[a]);
         }
@@ -369,6 +394,23 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
                 __syncwarp();
                 if (lane == 0)
                     for (int h = held; h >= 1; h--) mbar_arrive(&empty[(g - (uint32_t)h) % S]);
+            }
+        }
+    }
+finish:
+    if constexpr (PUSH) {
+        // last CTA of the grid tells the neighbours that this sweep (and its halo push) is complete
+        __syncthreads();
+        if (tid == 0 && (P.signal_flag[0] || P.signal_flag[1])) {
+            __threadfence_system();
+            const unsigned int prev = atomicAdd(P.done_counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *P.done_counter = 0u;
+                __threadfence_system();
+#pragma unroll
+                for (int i = 0; i < 2; i++)
+                    if (P.signal_flag[i])
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.signal_flag[i]), "l"(P.signal_value) : "memory");
             }
         }
     }

@@ -6,8 +6,9 @@ refresh ghosts:
 
   halo="push"  the sweep kernel stores the planes a neighbour needs straight into the
                neighbour's memory (CUDA-IPC peer pointer, NVLink); ordering between ranks is a
-               device-side flag per neighbour (b200_signal / b200_wait), no host round trip and
-               no collective on the data path;
+               flag per neighbour handled INSIDE the sweep kernel (spin at kernel start, release
+               store by the last CTA), the whole nt-loop is one C call (b200_slab_loop): no host
+               round trip and no collective on the data path;
   halo="nccl"  torch.distributed batched isend/irecv of the boundary planes after each sweep
                (also what the CPU/gloo tests use).
 
@@ -224,6 +225,40 @@ class SlabEngine:
                     ptrs[q] = self.mem[self.idxs[q]].ptr
                 capi.sweep_loop(self.test, self.real, nx, ny, ns, self.scalars, ptrs, niters, stream=stream,
                                 out_range=out_range)
+            for _ in range(niters):
+                if rot == 2:
+                    self.idxs[0], self.idxs[1] = self.idxs[1], self.idxs[0]
+                elif rot == 3:
+                    self.idxs = [self.idxs[1], self.idxs[2], self.idxs[0]]
+            self.sweeps_done += niters
+            return
+        if self.halo == "push" and b > a:
+            # fused halo push, neighbour ordering inside the sweep kernel, the whole loop in one C call
+            na = len(self.mem)
+            ptrs = [m.ptr for m in self.mem]
+            plo, phi = [0] * na, [0] * na
+            for q in range(rot):
+                ptrs[q] = self.mem[self.idxs[q]].ptr
+                if self.rank - 1 in self.peer:
+                    plo[q] = self.peer[self.rank - 1]["bufs"][self.idxs[q]]
+                if self.rank + 1 in self.peer:
+                    phi[q] = self.peer[self.rank + 1]["bufs"][self.idxs[q]]
+            peers = getattr(self, "_peer_layouts", None)
+            if peers is None:
+                peers = self._peer_layouts = {nb: SlabLayout(self.info, L.n, self.world, nb) for nb in self.peer}
+            push_lo, push_hi = (0, 0, 0), (0, 0, 0)
+            wait, sig = [0, 0], [0, 0]
+            if self.rank - 1 in self.peer:
+                n = peers[self.rank - 1]
+                push_lo = (L.send_lo()[0], n.own_hi - n.mem_lo, L.send_lo_cnt)
+                wait[0] = self.flags.ptr
+                sig[0] = self.peer[self.rank - 1]["flags"] + 8       # we are its upper neighbour
+            if self.rank + 1 in self.peer:
+                push_hi = (L.send_hi()[0], 0, L.send_hi_cnt)
+                wait[1] = self.flags.ptr + 8
+                sig[1] = self.peer[self.rank + 1]["flags"]           # we are its lower neighbour
+            capi.slab_loop(self.test, self.real, nx, ny, ns, self.scalars, ptrs, plo, phi, niters,
+                           self.sweeps_done, (a, b), push_lo, push_hi, wait, sig, stream=stream)
             for _ in range(niters):
                 if rot == 2:
                     self.idxs[0], self.idxs[1] = self.idxs[1], self.idxs[0]
