@@ -34,8 +34,11 @@
  *   laplacian w0,w1 | wave13pt w0,w1,w2 | divergence u,ux,uy,uz | gradient u,ux,uy,uz |
  *   uxx1 u0,u1,d1,xx,xy,xz | lapgsrb w0,w1 | jacobi w0,w1 | gaussblur w0,w1 |
  *   gameoflife u0,u1 | tricubic,tricubic2 u0,u1,a,b,c | vecadd w0,w1,w2 |
- *   matvec A,x,y | sincos x,y,xy
+ *   matvec A,x,y | sincos x,y,xy | matmul A,B,C
  * Layout: x fastest, index = i + nx*(j + ny*k).  2D tests use (nx, ny), ns = 1.
+ * matmul (matmul/matmul.F90:56-68, matmul/main.c:80-87): column-major A nx*ny, B ny*ns, C nx*ns;
+ * every sweep ACCUMULATES C += A*B (matmul/main.c:232-244).  Multi-GPU: columns of B and C are
+ * split, A is replicated; out_begin/out_end select a column range.
  *
  * There is NO CPU fallback: every entry point that computes fails with
  * B200_ERR_NO_DEVICE when no sm_100 device is usable.
@@ -54,7 +57,7 @@ extern "C" {
 typedef enum {
     B200_LAPLACIAN = 0, B200_WAVE13PT, B200_DIVERGENCE, B200_GRADIENT, B200_UXX1,
     B200_LAPGSRB, B200_JACOBI, B200_GAUSSBLUR, B200_GAMEOFLIFE, B200_TRICUBIC,
-    B200_TRICUBIC2, B200_VECADD, B200_MATVEC, B200_SINCOS, B200_NTESTS
+    B200_TRICUBIC2, B200_VECADD, B200_MATVEC, B200_SINCOS, B200_MATMUL, B200_NTESTS
 } b200_test_t;
 
 typedef enum { B200_F32 = 0, B200_F64 = 1 } b200_dtype_t;
@@ -89,7 +92,8 @@ int b200_test_by_name(const char* name);            /* -1 if unknown */
 const char* b200_last_error(void);
 int b200_api_version(void);
 
-/* Interior lattice-point updates per sweep for the given extents (0 if degenerate). */
+/* Interior lattice-point updates per sweep for the given extents (0 if degenerate).
+ * matvec: matrix elements; matmul: multiply-adds (nx*ny*ns, i.e. flops / 2). */
 unsigned long long b200_interior_points(int test, int nx, int ny, int ns);
 
 /* ---- device / environment ------------------------------------------------ */

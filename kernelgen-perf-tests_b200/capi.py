@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libb200stencil.so"
 
 TESTS = ["laplacian", "wave13pt", "divergence", "gradient", "uxx1", "lapgsrb", "jacobi",
-         "gaussblur", "gameoflife", "tricubic", "tricubic2", "vecadd", "matvec", "sincos"]
+         "gaussblur", "gameoflife", "tricubic", "tricubic2", "vecadd", "matvec", "sincos", "matmul"]
 TEST_ID = {n: i for i, n in enumerate(TESTS)}
 F32, F64 = 0, 1
 _DT = {"float": F32, "double": F64, "f32": F32, "f64": F64, np.float32: F32, np.float64: F64,

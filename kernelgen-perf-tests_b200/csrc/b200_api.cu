@@ -65,6 +65,7 @@ static const b200_test_info g_tests[B200_NTESTS] = {
     { "vecadd",     3, 3, 0, 3, {0, 0, 0}, {0, 0, 0}, 2, 1, 0, 0, -1 },  // vecadd/vecadd.c:66-83
     { "matvec",     2, 3, 0, 0, {0, 0, 0}, {0, 0, 0}, 1, 0, 0, 0, -1 },  // matvec/matvec.c:59-68
     { "sincos",     3, 3, 0, 0, {0, 0, 0}, {0, 0, 0}, 2, 1, 0, 0, -1 },  // sincos/sincos.F90:60-72
+    { "matmul",     3, 3, 0, 0, {0, 0, 0}, {0, 0, 0}, 3, 1, 0, 0, -1 },  // matmul/matmul.F90:56-68 (C is read and written)
 };
 
 typedef int (*launch_fn)(int, const HostArgs&);
@@ -72,11 +73,11 @@ typedef int (*info_fn)(int, KernelInfo*);
 static const launch_fn g_launch[B200_NTESTS] = {
     launch_laplacian, launch_wave13pt, launch_divergence, launch_gradient, launch_uxx1, launch_lapgsrb,
     launch_jacobi, launch_gaussblur, launch_gameoflife, launch_tricubic, launch_tricubic /* tricubic2: same kernel, other bounds */,
-    launch_vecadd, launch_matvec, launch_sincos };
+    launch_vecadd, launch_matvec, launch_sincos, launch_matmul };
 static const info_fn g_info[B200_NTESTS] = {
     info_laplacian, info_wave13pt, info_divergence, info_gradient, info_uxx1, info_lapgsrb,
     info_jacobi, info_gaussblur, info_gameoflife, info_tricubic, info_tricubic,
-    info_vecadd, info_matvec, info_sincos };
+    info_vecadd, info_matvec, info_sincos, info_matmul };
 
 // ------------------------------------------------------------------------------------------
 // device bookkeeping
@@ -213,6 +214,7 @@ unsigned long long b200_interior_points(int test, int nx, int ny, int ns)
     const b200_test_info* ti = b200_get_test_info(test);
     if (!ti) return 0;
     if (test == B200_MATVEC) return (unsigned long long)nx * ny;
+    if (test == B200_MATMUL) return (unsigned long long)nx * ny * (unsigned long long)ns;
     const long long ex = nx - ti->lo[0] - ti->hi[0], ey = ny - ti->lo[1] - ti->hi[1];
     const long long ez = ti->ndims == 3 ? ns - ti->lo[2] - ti->hi[2] : 1;
     if (ex <= 0 || ey <= 0 || ez <= 0) return 0;
@@ -493,6 +495,7 @@ int b200_plan(b200_ctx* c, int test, int dtype, int nx, int ny, int ns, const do
     c->split_n = ti->ndims == 3 ? c->ns : ny;
     c->unit = ti->ndims == 3 ? (size_t)nx * ny : (size_t)nx;
     if (test == B200_MATVEC) { c->split_n = ny; c->unit = (size_t)nx; }
+    if (test == B200_MATMUL) { c->split_n = ns; c->unit = (size_t)nx; }     // columns of B and C are split, A replicated
     // contiguous, near-equal slabs of the whole extent (boundary planes belong to the end slabs)
     const int G = c->ngpus;
     for (int g = 0; g < G; g++) {
@@ -519,11 +522,16 @@ static size_t slab_elems(const b200_ctx* c, const b200_slab& s, int slot)
         if (slot == 1) return (size_t)c->nx;                        // x is replicated
         if (slot == 2) return (size_t)(s.mem_hi - s.mem_lo);        // y rows
     }
+    if (c->test == B200_MATMUL) {
+        if (slot == 0) return (size_t)c->nx * c->ny;                // A is replicated
+        return (size_t)(slot == 1 ? c->ny : c->nx) * (size_t)(s.mem_hi - s.mem_lo);   // columns of B / C
+    }
     return c->unit * (size_t)(s.mem_hi - s.mem_lo);
 }
 static size_t slab_unit(const b200_ctx* c, int slot)
 {
     if (c->test == B200_MATVEC) return slot == 0 ? (size_t)c->nx : slot == 1 ? 0 : 1;
+    if (c->test == B200_MATMUL) return slot == 0 ? 0 : slot == 1 ? (size_t)c->ny : (size_t)c->nx;
     return c->unit;
 }
 
@@ -689,7 +697,7 @@ int b200_result_slot(const b200_ctx* c)
     switch (c->test) {
     case B200_DIVERGENCE: return 0;               // u       divergence.c:378-381
     case B200_GRADIENT:   return 1;               // ux (+uy,uz: slots 2,3)  gradient.c:388-391
-    default:              return 2;               // matvec y, sincos xy
+    default:              return 2;               // matvec y, sincos xy, matmul C
     }
 }
 

@@ -52,6 +52,8 @@ B200_DECLARE_OP(tricubic)
 B200_DECLARE_OP(vecadd)
 B200_DECLARE_OP(matvec)
 B200_DECLARE_OP(sincos)
+// the one dense contraction (k_matmul.cu)
+B200_DECLARE_OP(matmul)
 
 // Tensor-map (TMA descriptor) creation with a small cache; returns 0 on success.
 struct TmaBoxKey {

@@ -115,6 +115,8 @@ template <class Op> int launch_stream(const HostArgs& a)
 
     static const int env_serp = getenv("B200_SERPENTINE") ? atoi(getenv("B200_SERPENTINE")) : 1;
     P.reverse = env_serp ? (d.reverse_order & 1) : 0;
+    static const int env_cs = getenv("B200_STREAM_OUT") ? atoi(getenv("B200_STREAM_OUT")) : -1;
+    P.stream_out = env_cs >= 0 ? env_cs : (Op::STREAM_OUT ? 1 : 0);
     P.push_slot = -1;
     P.push_dim = ti->ndims == 3 ? 2 : 1;
     if (d.push_lo || d.push_hi) {

@@ -172,9 +172,9 @@ template <typename T> struct DivergenceOp {
 // plane) and uz of plane s = gamma*(C_p - C_{s-1}).  ring Cq[2]: Cq[PH&1] = C_{s-1}, Cq[(PH+1)&1] = C_s.
 // The three outputs are rewritten every sweep and never read: streamed past the L2.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct GradientOp {
+template <typename T, int TXV = 128> struct GradientOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 48 : 24), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
+    static constexpr int TX = TXV, TY = (sizeof(T) == 4 ? 48 : 24) * 128 / TXV, STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
     static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }

@@ -67,6 +67,7 @@ struct StreamParams {
     unsigned long long signal_value;
     unsigned int* done_counter;     // per-device CTA completion counter (library-owned, self-resetting)
     int reverse;                    // 1: walk the items in reverse order (serpentine sweeps)
+    int stream_out;                 // 1: outputs are never read back: store them with the streaming (evict-first) hint
 };
 
 struct alignas(64) TensorMaps {
@@ -166,7 +167,7 @@ template <class Op, bool PUSH> struct Ctx {
             VReg<T> r;
 #pragma unroll
             for (int v = 0; v < V; v++) r[v] = val[v];
-            if constexpr (Op::STREAM_OUT) __stcs(reinterpret_cast<uint4*>(dst), *reinterpret_cast<const uint4*>(r.v));
+            if (P.stream_out) __stcs(reinterpret_cast<uint4*>(dst), *reinterpret_cast<const uint4*>(r.v));
             else *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(r.v);
         } else {
 #pragma unroll

@@ -135,6 +135,7 @@ int main(int argc, char* argv[])
 	size_t szarray = (ndims == 3) ? (size_t)nx * ny * ns : (size_t)nx * ny;
 	for (int q = 0; q < na; q++) len[q] = szarray;
 	if (TEST == B200_MATVEC) { len[0] = (size_t)nx * ny; len[1] = (size_t)nx; len[2] = (size_t)ny; }
+	if (TEST == B200_MATMUL) { len[0] = (size_t)nx * ny; len[1] = (size_t)ny * ns; len[2] = (size_t)nx * ns; }  /* matmul/main.c:80-85 */
 	size_t szarrayb = szarray * sizeof(real);
 
 	real* a[B200_MAX_ARRAYS] = { 0 };
@@ -161,6 +162,16 @@ int main(int argc, char* argv[])
 		for (int i = 0; i < nx; i++) { a[1][i] = real_rand(); xmean += a[1][i]; }
 		for (int i = 0; i < ny; i++) { a[2][i] = real_rand(); ymean += a[2][i]; }
 		if (!no_timing) printf("initial mean = %f\n", amean / (nx * ny) + xmean / nx + ymean / ny);
+	}
+	else if (TEST == B200_MATMUL)
+	{
+		/* matmul/main.c:98-110: A, then B; printed unconditionally.  The reference never
+		 * initialises C (fresh memalign pages read as zero); it is zeroed explicitly here. */
+		real meanA = 0.0f, meanB = 0.0f;
+		for (size_t i = 0; i < len[0]; i++) { a[0][i] = real_rand(); meanA += a[0][i]; }
+		for (size_t i = 0; i < len[1]; i++) { a[1][i] = real_rand(); meanB += a[1][i]; }
+		memset(a[2], 0, len[2] * sizeof(real));
+		printf("initial mean = %f\n", (meanA / len[0] + meanB / len[1]));
 	}
 	else
 	{
@@ -249,6 +260,9 @@ int main(int argc, char* argv[])
 		double lups = (double)b200_interior_points(TEST, nx, ny, ns);
 		double sec = st.kernel_ms_per_sweep * 1e-3;
 		double bytes = lups * (ti->nread + ti->nwritten) * sizeof(real);
+		if (TEST == B200_MATMUL)
+			printf("b200: %d GPU(s), %.3f TFLOP/s (2*nx*ny*ns flops per sweep)\n", st.ngpus, 2 * lups / sec * 1e-12);
+		else
 		printf("b200: %d GPU(s), %.3f GLUP/s, %.1f GB/s algorithmic (%d+%d arrays x %d bytes per LUP)\n",
 			st.ngpus, lups / sec * 1e-9, bytes / sec * 1e-9, ti->nread, ti->nwritten, (int)sizeof(real));
 	}
@@ -259,6 +273,12 @@ int main(int argc, char* argv[])
 		real ymean = 0.0f;
 		for (int i = 0; i < ny; i++) ymean += a[2][i];
 		printf("final mean = %f\n", ymean / ny);
+	}
+	else if (TEST == B200_MATMUL)
+	{
+		real meanC = 0.0f;                                 /* matmul/main.c:311-314 */
+		for (size_t i = 0; i < len[2]; i++) meanC += a[2][i];
+		printf("final mean = %f\n", meanC / len[2]);
 	}
 	else if (TEST == B200_GRADIENT)
 	{

@@ -124,6 +124,8 @@ class SlabEngine:
         self.unit = nx * ny if info["ndims"] == 3 else nx            # elements per plane / row
         if test == "matvec":
             self.unit = nx
+        if test == "matmul":
+            self.unit = nx          # columns of C; B's columns hold ny elements, A is replicated
         self.stream = torch.cuda.current_stream()
         # buffers: slab incl. ghosts, from the C ABI allocator (IPC-exportable)
         self.mem, self.t = [], []
@@ -151,6 +153,8 @@ class SlabEngine:
     def _slot_len(self, q):
         if self.test == "matvec":
             return [self.nx * self.layout.mem_n, self.nx, self.layout.mem_n][q]
+        if self.test == "matmul":
+            return [self.nx * self.ny, self.ny * self.layout.mem_n, self.nx * self.layout.mem_n][q]
         return self.unit * self.layout.mem_n
 
     def local_dims(self):
@@ -164,6 +168,8 @@ class SlabEngine:
         i = self.info
         if self.test == "matvec":
             return self.nx * (b - a)
+        if self.test == "matmul":
+            return self.nx * self.ny * (b - a)
         ex = self.nx - i["lo"][0] - i["hi"][0]
         ey = (self.ny - i["lo"][1] - i["hi"][1]) if i["ndims"] == 3 else 1
         return max(ex, 0) * max(ey, 0) * max(b - a, 0)
@@ -216,7 +222,7 @@ class SlabEngine:
         out_pos = 2 if rot == 3 else 1
         stream = self.stream.cuda_stream
         a, b = L.out_range()
-        out_range = (a, b) if (self.world > 1 or self.test in ("vecadd", "sincos", "matvec")) else None
+        out_range = (a, b) if (self.world > 1 or self.test in ("vecadd", "sincos", "matvec", "matmul")) else None
         if not self.exchange:
             # no ghost refresh between sweeps: the whole nt-loop is enqueued by one C call
             if b > a:
@@ -304,6 +310,8 @@ class SlabEngine:
         L, torch = self.layout, self.torch
         if self.test == "matvec":
             part = {0: full[L.mem_lo * self.nx:L.mem_hi * self.nx], 1: full, 2: full[L.mem_lo:L.mem_hi]}[q]
+        elif self.test == "matmul":
+            part = {0: full, 1: full[L.mem_lo * self.ny:L.mem_hi * self.ny], 2: full[L.mem_lo * self.nx:L.mem_hi * self.nx]}[q]
         else:
             part = full[L.mem_lo * self.unit:L.mem_hi * self.unit]
         self.t[q].copy_(torch.from_numpy(np.ascontiguousarray(part)).to(self.t[q].device))
@@ -315,6 +323,10 @@ class SlabEngine:
             if q == 1:
                 return self.t[q].cpu().numpy()
             u = self.nx if q == 0 else 1
+        elif self.test == "matmul":
+            if q == 0:
+                return self.t[q].cpu().numpy()
+            u = self.ny if q == 1 else self.nx
         else:
             u = self.unit
         a, b = (L.own_lo - L.mem_lo) * u, (L.own_hi - L.mem_lo) * u
@@ -417,6 +429,8 @@ def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3):
     sizes = [("C1", (512, 256, 256))] + ([("C2", (1024, 1024, 512))] if full else [])
     for label, (nx, ny, ns) in sizes:
         for test in pkg.TESTS:
+            if test == "matmul":        # tensor-core bound, not HBM: see matmul_table()
+                continue
             info = pkg.test_info(test)
             for real in ("double", "float"):
                 dims = (nx, ny, ns) if info["ndims"] == 3 else (nx, ny * ns, 1)

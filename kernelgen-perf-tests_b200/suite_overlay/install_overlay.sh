@@ -15,7 +15,7 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 B200_ROOT="${2:-$(cd "$HERE/../.." && pwd)}"
 [ -f "$SUITE/benchmark" ] && [ -f "$SUITE/makefile.in" ] || { echo "usage: $0 <kernelgen-perf-tests checkout>"; exit 1; }
 
-TESTS3D="laplacian wave13pt divergence gradient uxx1 lapgsrb tricubic tricubic2 vecadd sincos"
+TESTS3D="laplacian wave13pt divergence gradient uxx1 lapgsrb tricubic tricubic2 vecadd sincos matmul"
 TESTS2D="jacobi gaussblur gameoflife matvec"
 
 for t in $TESTS3D $TESTS2D; do

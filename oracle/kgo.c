@@ -17,7 +17,7 @@
  *  laplacian w0,w1 | wave13pt w0,w1,w2 | divergence u,ux,uy,uz |
  *  gradient u,ux,uy,uz | uxx1 u0,u1,d1,xx,xy,xz | lapgsrb w0,w1 |
  *  jacobi w0,w1 | gaussblur w0,w1 | gameoflife u0,u1 | tricubic[2] u0,u1,a,b,c |
- *  vecadd w0,w1,w2 | matvec A,x,y | sincos x,y,xy */
+ *  vecadd w0,w1,w2 | matvec A,x,y | sincos x,y,xy | matmul A,B,C */
 static const kgo_test_info g_tests[KGO_NTESTS] = {
     { "laplacian",  3, 2, 2, 2 },
     { "wave13pt",   3, 3, 3, 3 },
@@ -33,6 +33,7 @@ static const kgo_test_info g_tests[KGO_NTESTS] = {
     { "vecadd",     3, 3, 0, 3 },
     { "matvec",     2, 3, 0, 0 },
     { "sincos",     3, 3, 0, 0 },
+    { "matmul",     3, 3, 0, 0 },
 };
 
 const kgo_test_info* kgo_info(int test)
@@ -58,6 +59,8 @@ size_t kgo_array_len(int test, int slot, int nx, int ny, int ns)
     if (!ti || slot < 0 || slot >= ti->narrays) return 0;
     if (test == KGO_MATVEC)
         return slot == 0 ? (size_t)nx * ny : slot == 1 ? (size_t)nx : (size_t)ny;
+    if (test == KGO_MATMUL)     /* A nx*ny, B ny*ns, C nx*ns  (matmul/main.c:80-87) */
+        return slot == 0 ? (size_t)nx * ny : slot == 1 ? (size_t)ny * ns : (size_t)nx * ns;
     return ti->ndims == 3 ? (size_t)nx * ny * ns : (size_t)nx * ny;
 }
 
@@ -119,7 +122,7 @@ int kgo_run(int test, int dtype, int nx, int ny, int ns, int nt,
     {
     case KGO_DIVERGENCE: return 0;                /* u */
     case KGO_GRADIENT:   return 1;                /* ux (+uy+uz) */
-    default:             return 2;                /* matvec y, sincos xy */
+    default:             return 2;                /* matvec y, sincos xy, matmul C */
     }
 }
 

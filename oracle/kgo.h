@@ -27,7 +27,7 @@ extern "C" {
 enum {
     KGO_LAPLACIAN = 0, KGO_WAVE13PT, KGO_DIVERGENCE, KGO_GRADIENT, KGO_UXX1,
     KGO_LAPGSRB, KGO_JACOBI, KGO_GAUSSBLUR, KGO_GAMEOFLIFE, KGO_TRICUBIC,
-    KGO_TRICUBIC2, KGO_VECADD, KGO_MATVEC, KGO_SINCOS, KGO_NTESTS
+    KGO_TRICUBIC2, KGO_VECADD, KGO_MATVEC, KGO_SINCOS, KGO_MATMUL, KGO_NTESTS
 };
 enum { KGO_F32 = 0, KGO_F64 = 1 };
 

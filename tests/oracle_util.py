@@ -18,7 +18,7 @@ ORACLE_DIR = ROOT / "oracle"
 REF_DIR = ORACLE_DIR / "_ref"
 
 TESTS = ["laplacian", "wave13pt", "divergence", "gradient", "uxx1", "lapgsrb", "jacobi",
-         "gaussblur", "gameoflife", "tricubic", "tricubic2", "vecadd", "matvec", "sincos"]
+         "gaussblur", "gameoflife", "tricubic", "tricubic2", "vecadd", "matvec", "sincos", "matmul"]
 TEST_ID = {n: i for i, n in enumerate(TESTS)}
 F32, F64 = 0, 1
 NP_DTYPE = {F32: np.float32, F64: np.float64, "float": np.float32, "double": np.float64}

@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 BIN = ROOT / "kernelgen-perf-tests_b200" / "drivers" / "bin"
 NUM = r"[-+]?[0-9]*\.?[0-9]+(?:[eE][-+]?[0-9]+)?"
 TESTS = ["laplacian", "wave13pt", "divergence", "gradient", "uxx1", "lapgsrb", "jacobi",
-         "gaussblur", "gameoflife", "tricubic", "tricubic2", "vecadd", "matvec", "sincos"]
+         "gaussblur", "gameoflife", "tricubic", "tricubic2", "vecadd", "matvec", "sincos", "matmul"]
 TWO_D = {"jacobi", "gaussblur", "gameoflife", "matvec"}
 
 

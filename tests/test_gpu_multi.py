@@ -21,7 +21,7 @@ CASES = [("laplacian", (130, 20, 31)), ("wave13pt", (128, 24, 40)), ("lapgsrb", 
          ("tricubic", (64, 18, 29)), ("tricubic2", (64, 18, 29)), ("uxx1", (66, 18, 27)),
          ("divergence", (64, 18, 27)), ("gradient", (64, 18, 27)), ("vecadd", (64, 18, 27)),
          ("jacobi", (130, 211, 1)), ("gaussblur", (128, 190, 1)), ("gameoflife", (66, 175, 1)),
-         ("matvec", (128, 301, 1)), ("sincos", (32, 18, 21))]
+         ("matvec", (128, 301, 1)), ("sincos", (32, 18, 21)), ("matmul", (130, 70, 150))]
 SCAL = {"laplacian": [0.3, 0.1], "wave13pt": [0.6, -0.03, 0.09], "lapgsrb": [0.5, 0.03, 0.02, -0.01],
         "uxx1": [0.4, -0.2], "divergence": [0.6, -0.2, 0.5], "gradient": [0.6, -0.2, 0.5],
         "jacobi": [0.5, 0.1, 0.02], "gaussblur": [0.6, 0.2, 0.1, 0.05, 0.03, 0.01]}

@@ -120,6 +120,52 @@ def test_readme_size_double(ctx, pkg, test):
     assert "%f" % fm_gpu == "%f" % fm_ref
 
 
+MATMUL_SIZES = [(128, 128, 128), (256, 64, 384), (130, 37, 29), (131, 67, 259), (16, 5, 5), (5, 5, 5), (1, 1, 1), (300, 513, 140)]
+
+
+@pytest.mark.parametrize("mode", ["tensor", "cublas"])
+@pytest.mark.parametrize("real", ["float", "double"])
+def test_matmul_vs_oracle(ctx, oracle, real, mode, monkeypatch):
+    """matmul/matmul.F90:56-68 -- C += A*B over nt sweeps (C accumulates, matmul/main.c:232-244):
+    the hand-written DMMA / 3xTF32 kernels (aligned and element-wise loaders, ragged tiles) and the
+    cuBLAS baseline against the sequential-sum restatement; also with a non-zero initial C."""
+    if mode == "cublas":
+        monkeypatch.setenv("B200_MATMUL", "cublas")
+    else:
+        monkeypatch.delenv("B200_MATMUL", raising=False)
+    rng = np.random.default_rng(5)
+    for nx, ny, ns in MATMUL_SIZES:
+        for nt in (1, 3):
+            scalars, inputs, _ = oracle.init("matmul", real, nx, ny, ns)
+            if nt == 3:
+                inputs[2][:] = rng.uniform(-1, 1, inputs[2].size).astype(inputs[2].dtype)
+            want = [a.copy() for a in inputs]
+            slot_o = oracle.run("matmul", real, nx, ny, ns, nt, scalars, want)
+            slot, got, stats = gpu_run(ctx, "matmul", real, nx, ny, ns, nt, scalars, inputs)
+            assert slot == slot_o == 2
+            assert np.array_equal(got[0], inputs[0]) and np.array_equal(got[1], inputs[1])
+            e = normwise(got[2], want[2])
+            assert e <= TOL[real], f"matmul/{real}/{mode} {nx}x{ny}x{ns} nt={nt}: normwise error {e:.3e}"
+
+
+def test_matmul_1024_float_accuracy(ctx):
+    """3xTF32 keeps FP32-level accuracy where one TF32 pass would not: 1024^3 against a float64
+    product of the same float32 inputs (a size the sequential oracle would take too long on)."""
+    rng = np.random.default_rng(11)
+    n = 1024
+    A = rng.uniform(-1, 1, n * n).astype(np.float32)
+    B = rng.uniform(-1, 1, n * n).astype(np.float32)
+    Cm = np.zeros(n * n, np.float32)
+    slot, got, _ = gpu_run(ctx, "matmul", "float", n, n, n, 1, [], [A, B, Cm])
+    ref = (A.reshape(n, n).T.astype(np.float64) @ B.reshape(n, n).T.astype(np.float64)).T.reshape(-1)
+    e = float(np.max(np.abs(got[2] - ref)) / np.max(np.abs(ref)))
+    assert e <= 2e-6, e
+    Ad, Bd = A.astype(np.float64), B.astype(np.float64)
+    slot, gotd, _ = gpu_run(ctx, "matmul", "double", n, n, n, 1, [], [Ad, Bd, np.zeros(n * n)])
+    ed = float(np.max(np.abs(gotd[2] - ref)) / np.max(np.abs(ref)))
+    assert ed <= 1e-14, ed
+
+
 def test_degenerate_and_errors(ctx, pkg):
     a = [np.ones(27), np.ones(27) * 2]
     slot, got, _ = gpu_run(ctx, "wave13pt", "double", 3, 3, 3, 2, [0.1, 0.2, 0.3], a + [np.ones(27) * 3])
