@@ -281,6 +281,8 @@ def main():
     want_suite = args.suite if args.suite != "auto" else ("full" if world == 1 else "none")
     if rank == 0 and world == 1 and want_suite != "none":
         suite = slabmod.suite_table(pkg, peak, full=(want_suite == "full"), scalars=DEFAULT_SCALARS)
+        if want_suite == "full":
+            suite += slabmod.matmul_table(pkg)
 
     if rank == 0:
         line = {

@@ -12,7 +12,8 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libb200stencil.so"
+# B200_LIB selects an experiment build of the same library (tools/ A/B measurements); default: the product
+LIB_PATH = Path(os.environ["B200_LIB"]) if os.environ.get("B200_LIB") else PKG_DIR / "libb200stencil.so"
 
 TESTS = ["laplacian", "wave13pt", "divergence", "gradient", "uxx1", "lapgsrb", "jacobi",
          "gaussblur", "gameoflife", "tricubic", "tricubic2", "vecadd", "matvec", "sincos", "matmul"]

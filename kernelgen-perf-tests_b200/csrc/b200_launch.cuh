@@ -27,7 +27,7 @@ template <class Op, bool PUSH> struct KernelSetup {
             B200_CUDA(cudaFuncSetAttribute(stream_kernel<Op, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Geo<Op>::SMEM_BYTES));
             int n = 0;
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stream_kernel<Op, PUSH>, NTHREADS,
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stream_kernel<Op, PUSH>, Geo<Op>::NTHREADS,
                                                                     Geo<Op>::SMEM_BYTES));
             if (n < 1) { set_error("kernel does not fit on an SM"); return B200_ERR_CUDA; }
             blocks_per_sm[device] = n;
@@ -115,8 +115,6 @@ template <class Op> int launch_stream(const HostArgs& a)
 
     static const int env_serp = getenv("B200_SERPENTINE") ? atoi(getenv("B200_SERPENTINE")) : 1;
     P.reverse = env_serp ? (d.reverse_order & 1) : 0;
-    static const int env_cs = getenv("B200_STREAM_OUT") ? atoi(getenv("B200_STREAM_OUT")) : -1;
-    P.stream_out = env_cs >= 0 ? env_cs : (Op::STREAM_OUT ? 1 : 0);
     P.push_slot = -1;
     P.push_dim = ti->ndims == 3 ? 2 : 1;
     if (d.push_lo || d.push_hi) {
@@ -151,8 +149,8 @@ template <class Op> int launch_stream(const HostArgs& a)
     }
 
     const int grid = (int)(items < grid_cap ? items : grid_cap);
-    if (push) stream_kernel<Op, true><<<grid, NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
-    else stream_kernel<Op, false><<<grid, NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
+    if (push) stream_kernel<Op, true><<<grid, G::NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
+    else stream_kernel<Op, false><<<grid, G::NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
     B200_CUDA(cudaGetLastError());
     count_launch();
     return B200_OK;

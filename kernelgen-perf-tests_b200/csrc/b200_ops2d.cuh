@@ -16,7 +16,8 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct JacobiOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 96 : 48, NC, 128), STAGES = 4, HOLD = 0, WARM = 0, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 0, 0}; }
@@ -56,7 +57,8 @@ template <typename T> struct JacobiOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct GaussblurOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 96 : 48, NC, 128), STAGES = 4, HOLD = 0, WARM = 0, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 2, 2, 0, 0}; }
@@ -113,7 +115,8 @@ template <typename T> struct GaussblurOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct GameoflifeOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 96 : 48), STAGES = 4, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 96 : 48, NC, 128), STAGES = 4, HOLD = 0, WARM = 0, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 0, 0}; }

@@ -23,7 +23,8 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct LaplacianOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 48 : 24), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 1;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
@@ -71,7 +72,8 @@ template <typename T> struct LaplacianOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct Wave13ptOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 6, HOLD = 0, WARM = 4, PERIOD = 2;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 4, PERIOD = 2;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 2;
     static constexpr StagedSpec spec(int a)
@@ -125,7 +127,8 @@ template <typename T> struct Wave13ptOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct DivergenceOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 5, HOLD = 0, WARM = 2, PERIOD = 2;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 5, HOLD = 0, WARM = 2, PERIOD = 2;
     static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 3;
     static constexpr StagedSpec spec(int a)
@@ -172,9 +175,10 @@ template <typename T> struct DivergenceOp {
 // plane) and uz of plane s = gamma*(C_p - C_{s-1}).  ring Cq[2]: Cq[PH&1] = C_{s-1}, Cq[(PH+1)&1] = C_s.
 // The three outputs are rewritten every sweep and never read: streamed past the L2.
 // ------------------------------------------------------------------------------------------
-template <typename T, int TXV = 128> struct GradientOp {
+template <typename T> struct GradientOp {
     using real = T;
-    static constexpr int TX = TXV, TY = (sizeof(T) == 4 ? 48 : 24) * 128 / TXV, STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
     static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
@@ -227,7 +231,8 @@ template <typename T, int TXV = 128> struct GradientOp {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct Uxx1Op {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 12 : 6), STAGES = 5, HOLD = 0, WARM = 3, PERIOD = 3;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 12 : 6, NC, 128), STAGES = 5, HOLD = 0, WARM = 3, PERIOD = 3;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 5;
     static constexpr StagedSpec spec(int a)
@@ -299,7 +304,8 @@ template <typename T> struct Uxx1Op {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct LapgsrbOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 24 : 12), STAGES = 8, HOLD = 0, WARM = 4, PERIOD = 2;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 8, HOLD = 0, WARM = 4, PERIOD = 2;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 2, 2, 2, 2}; }
@@ -366,7 +372,8 @@ template <typename T> B200_DEV void cubic_weights(T t, T (&w)[4])
 
 template <typename T> struct TricubicOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 12 : 6), STAGES = 6, HOLD = 3, WARM = 3, PERIOD = 1;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 12 : 6, NC, 128), STAGES = 6, HOLD = 3, WARM = 3, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 4;
     static constexpr StagedSpec spec(int a)

@@ -25,8 +25,20 @@
 
 namespace b200 {
 
-constexpr int NCONS = 384;              // consumer threads (12 warps), one CTA per SM
-constexpr int NTHREADS = NCONS + 32;    // + 1 producer warp
+// Consumer threads per CTA (one CTA per SM, + 1 producer warp) are chosen per Op (Op::NC):
+//   384 (12 warps): 13 warps = 4+3+3+3 over the four SM sub-partitions, 128 registers per thread;
+//   512 (16 warps): 17 warps put 5 on one sub-partition -> 96 registers per thread; for the Ops that
+//                   fit, a third more warps hide more latency and keep more stores in flight.
+#ifndef B200_EXP_NC32
+#define B200_EXP_NC32 0
+#endif
+#ifndef B200_EXP_NC64
+#define B200_EXP_NC64 0
+#endif
+// consumer threads of an Op: its own choice unless an experiment build overrides it (-DB200_EXP_NC32/64=384|512)
+template <typename T> constexpr int pick_nc(int own) { return sizeof(T) == 4 ? (B200_EXP_NC32 ? B200_EXP_NC32 : own) : (B200_EXP_NC64 ? B200_EXP_NC64 : own); }
+// tile height: the Op's preferred TY rounded up to a whole number of thread rows (NC / (TX / V))
+template <typename T> constexpr int pick_ty(int want, int nc, int tx) { return (want + nc / (tx / (16 / (int)sizeof(T))) - 1) / (nc / (tx / (16 / (int)sizeof(T)))) * (nc / (tx / (16 / (int)sizeof(T)))); }
 constexpr int MAX_STAGED = 5;
 constexpr int MAX_STAGES = 8;           // 2*MAX_STAGES mbarriers fit the 128-byte header
 
@@ -67,7 +79,6 @@ struct StreamParams {
     unsigned long long signal_value;
     unsigned int* done_counter;     // per-device CTA completion counter (library-owned, self-resetting)
     int reverse;                    // 1: walk the items in reverse order (serpentine sweeps)
-    int stream_out;                 // 1: outputs are never read back: store them with the streaming (evict-first) hint
 };
 
 struct alignas(64) TensorMaps {
@@ -83,9 +94,11 @@ template <class Op> struct Geo {
     static constexpr int TX = Op::TX;
     static constexpr int TY = Op::TY;
     static constexpr int LX = TX / V;            // threads along x
-    static constexpr int LY = NCONS / LX;        // thread rows
+    static constexpr int NC = Op::NC;            // consumer threads
+    static constexpr int NTHREADS = NC + 32;     // + the producer warp
+    static constexpr int LY = NC / LX;           // thread rows
     static constexpr int CPT = TY / LY;          // rows ("columns" in z) per thread
-    static_assert(TX % V == 0 && NCONS % LX == 0 && TY % LY == 0, "bad tile");
+    static_assert((NC == 384 || NC == 512) && TX % V == 0 && NC % LX == 0 && TY % LY == 0, "bad tile");
     static constexpr int hxp(int a) { return Op::spec(a).hx ? V : 0; }
     static constexpr int bw(int a) { return TX + 2 * hxp(a); }
     static constexpr int bh(int a) { return TY + Op::spec(a).ylo + Op::spec(a).yhi; }
@@ -167,7 +180,7 @@ template <class Op, bool PUSH> struct Ctx {
             VReg<T> r;
 #pragma unroll
             for (int v = 0; v < V; v++) r[v] = val[v];
-            if (P.stream_out) __stcs(reinterpret_cast<uint4*>(dst), *reinterpret_cast<const uint4*>(r.v));
+            if constexpr (Op::STREAM_OUT) __stcs(reinterpret_cast<uint4*>(dst), *reinterpret_cast<const uint4*>(r.v));
             else *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(r.v);
         } else {
 #pragma unroll
@@ -289,10 +302,10 @@ template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int i
 // (4+3+3+3) can have the full 128 registers per thread, while 16+1 warps or 2 CTAs x (8+1) warps
 // put 5 warps on one sub-partition and are limited to 96 -- which spills in every double kernel
 // (measured: profiles/README.md).
-template <class Op> struct RegCap { static constexpr int value = 128; };
+template <class Op> struct RegCap { static constexpr int value = Op::NC == 512 ? 96 : 128; };
 
 template <class Op, bool PUSH>
-__global__ void __launch_bounds__(NTHREADS) __maxnreg__(RegCap<Op>::value)
+__global__ void __launch_bounds__(Geo<Op>::NTHREADS) __maxnreg__(RegCap<Op>::value)
 stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ TensorMaps M)
 {
     using G = Geo<Op>;
@@ -310,7 +323,7 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
 #pragma unroll
         for (int i = 0; i < S; i++) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], NCONS / 32);
+            mbar_init(&empty[i], G::NC / 32);
         }
         mbar_fence_init();
         if constexpr (PUSH) {
@@ -334,7 +347,7 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
     }
     __syncthreads();
 
-    if (warp == NCONS / 32) {
+    if (warp == G::NC / 32) {
         // ------------------------------ producer warp ------------------------------
         if (P.use_tma) {
             if (lane != 0) goto finish;

@@ -68,7 +68,8 @@ template <typename T> static int launch_fanout(const HostArgs& a, int mode)
 // ux, uy, uz -- without (4) / with (5) gradient's halo'd tile: the engine's ceiling for 1 read + 3 writes
 template <typename T, int HALO> struct EngineFanoutOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 48 : 24), STAGES = 6, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 0, PERIOD = 1;
     static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, HALO, HALO, HALO, 0, 0}; }

@@ -27,7 +27,8 @@ int info_laplacian(int dtype, KernelInfo* ki)
 namespace b200 {
 template <typename T, int HALO> struct EngineCopyOp {
     using real = T;
-    static constexpr int TX = 128, TY = (sizeof(T) == 4 ? 48 : 24), STAGES = 6, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 0, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, HALO, HALO, HALO, 0, 0}; }

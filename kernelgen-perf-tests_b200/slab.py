@@ -135,7 +135,7 @@ class SlabEngine:
             n = self._slot_len(q)
             m = _DevMem(pkg, n, self.np_dtype)
             t = m.tensor(torch)
-            t.copy_(torch.rand(n, generator=g, device="cuda", dtype=t.dtype) * 2 - 1)
+            t.uniform_(-1.0, 1.0, generator=g)           # in place: no temporaries next to 30+ GB slabs
             self.mem.append(m)
             self.t.append(t)
         self.idxs = [0, 1, 2]
@@ -426,13 +426,14 @@ def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3):
     """GLUP/s and fraction of the HBM roofline for every test, float and double, on cuda:0."""
     import torch
     rows = []
-    sizes = [("C1", (512, 256, 256))] + ([("C2", (1024, 1024, 512))] if full else [])
+    # C1 = the README size, C2 = BASELINE configs[2], C3 = the ">= 1024^3 double grid" of the north star
+    sizes = [("C1", (512, 256, 256))] + ([("C2", (1024, 1024, 512)), ("C3", (1024, 1024, 1024))] if full else [])
     for label, (nx, ny, ns) in sizes:
         for test in pkg.TESTS:
             if test == "matmul":        # tensor-core bound, not HBM: see matmul_table()
                 continue
             info = pkg.test_info(test)
-            for real in ("double", "float"):
+            for real in (("double",) if label == "C3" else ("double", "float")):
                 dims = (nx, ny, ns) if info["ndims"] == 3 else (nx, ny * ns, 1)
                 try:
                     eng = SlabEngine(pkg, test, real, dims[0], dims[1], dims[2], scalars.get(test, []))
@@ -455,4 +456,46 @@ def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3):
                 except Exception as e:      # keep the headline alive; report the failure
                     rows.append({"test": test, "real": real, "cfg": label, "error": str(e)[:200]})
                     torch.cuda.synchronize()
+    return rows
+
+
+def matmul_table(pkg, n=8192, reps=3):
+    """TFLOP/s of the matmul test (C += A*B, n^3, BASELINE configs[4]) through b200_sweep_loop: the
+    hand-written tensor-core kernels, and the cuBLAS baseline (B200_MATMUL=cublas) beside them."""
+    import os
+    import torch
+    rows = []
+    stream = torch.cuda.current_stream().cuda_stream
+    for real, dt in (("double", torch.float64), ("float", torch.float32)):
+        try:
+            A = torch.rand(n * n, device="cuda", dtype=dt) * 2 - 1
+            B = torch.rand(n * n, device="cuda", dtype=dt) * 2 - 1
+            row = {"test": "matmul", "real": real, "size": f"{n}x{n}x{n}", "regs": pkg.kernel_info("matmul", real)["regs"]}
+            for mode in ("tensor", "cublas"):
+                if mode == "cublas":
+                    os.environ["B200_MATMUL"] = "cublas"
+                else:
+                    os.environ.pop("B200_MATMUL", None)
+                Cm = torch.zeros(n * n, device="cuda", dtype=dt)
+                ptrs = [A.data_ptr(), B.data_ptr(), Cm.data_ptr()]
+                pkg.capi.sweep_loop("matmul", real, n, n, n, [], ptrs, 1, stream=stream)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pkg.capi.sweep_loop("matmul", real, n, n, n, [], ptrs, reps, stream=stream)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                key = "tflops" if mode == "tensor" else "cublas_tflops"
+                row[key] = round(2 * n ** 3 / ms / 1e9, 2)
+                if mode == "tensor":
+                    row["ms_per_sweep"] = round(ms, 3)
+                del Cm
+            row["vs_cublas"] = round(row["tflops"] / row["cublas_tflops"], 3)
+            rows.append(row)
+        except Exception as e:
+            rows.append({"test": "matmul", "real": real, "error": str(e)[:200]})
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("B200_MATMUL", None)
     return rows

@@ -12,6 +12,10 @@ if d.get("cpu_baseline"):
     print("cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"], d["cpu_baseline"]["kind"])
 tab = {}
 for r in s:
+    if r["test"] == "matmul":
+        print("matmul", r)
+        continue
     tab.setdefault(r["test"], {})[(r["cfg"], r["real"])] = r.get("frac", r.get("error", "?"))
 for t, v in tab.items():
-    print(f"{t:11s} C1 d {v.get(('C1','double'))!s:7} f {v.get(('C1','float'))!s:7} | C2 d {v.get(('C2','double'))!s:7} f {v.get(('C2','float'))!s:7}")
+    print(f"{t:11s} C1 d {v.get(('C1','double'))!s:7} f {v.get(('C1','float'))!s:7} | C2 d {v.get(('C2','double'))!s:7} f {v.get(('C2','float'))!s:7}"
+          f" | C3 d {v.get(('C3','double'))!s:7}")
