@@ -133,7 +133,8 @@ int get_tensor_map(const TmaBoxKey& key, void* out_map)
     memset(&e, 0, sizeof(e));
     e.key = key;
     const cuuint64_t dims[3] = { (cuuint64_t)key.nx, (cuuint64_t)key.ny, (cuuint64_t)key.ns };
-    const cuuint64_t strides[2] = { (cuuint64_t)key.nx * key.esz, (cuuint64_t)key.nx * key.ny * key.esz };
+    const cuuint64_t px = key.px ? key.px : key.nx, py = key.py ? key.py : key.ny;
+    const cuuint64_t strides[2] = { px * key.esz, px * py * key.esz };
     const cuuint32_t box[3] = { (cuuint32_t)key.bw, (cuuint32_t)key.bh, 1u };
     const cuuint32_t estr[3] = { 1u, 1u, 1u };
     const CUresult r = g_encode(&e.map, key.esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,

@@ -66,6 +66,18 @@ B200_DEV void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
         : "memory");
 }
 
+// shared -> global tile store (bulk async-group completion); out-of-range parts of the box are not written
+B200_DEV void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+B200_DEV void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> B200_DEV void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+B200_DEV void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before it is signalled
+B200_DEV void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // L2 cache-policy descriptors for the .L2::cache_hint operand (same encodings CUTLASS uses)
 constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t L2_EVICT_FIRST  = 0x12F0000000000000ull;

@@ -58,7 +58,8 @@ B200_DECLARE_OP(matmul)
 // Tensor-map (TMA descriptor) creation with a small cache; returns 0 on success.
 struct TmaBoxKey {
     const void* ptr;
-    int nx, ny, ns, esz, bw, bh;
+    int nx, ny, ns, esz, bw, bh;   // tensor extents (elements), element size, box
+    int px, py;                    // pitches: elements per row, rows per plane (0 = nx, ny)
 };
 int get_tensor_map(const TmaBoxKey& key, void* out_map /* CUtensorMap* */);
 

@@ -15,7 +15,7 @@
 
 namespace b200 {
 
-template <class Op, bool PUSH> struct KernelSetup {
+template <class Op, bool PUSH, bool TS> struct KernelSetup {
     bool done[16] = {};
     int blocks_per_sm[16] = {};
     std::mutex mu;
@@ -24,10 +24,10 @@ template <class Op, bool PUSH> struct KernelSetup {
         std::lock_guard<std::mutex> lk(mu);
         if (device < 0 || device >= 16) { set_error("device index %d out of range", device); return B200_ERR_ARG; }
         if (!done[device]) {
-            B200_CUDA(cudaFuncSetAttribute(stream_kernel<Op, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            B200_CUDA(cudaFuncSetAttribute(stream_kernel<Op, PUSH, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Geo<Op>::SMEM_BYTES));
             int n = 0;
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stream_kernel<Op, PUSH>, Geo<Op>::NTHREADS,
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stream_kernel<Op, PUSH, TS>, Geo<Op>::NTHREADS,
                                                                     Geo<Op>::SMEM_BYTES));
             if (n < 1) { set_error("kernel does not fit on an SM"); return B200_ERR_CUDA; }
             blocks_per_sm[device] = n;
@@ -38,9 +38,9 @@ template <class Op, bool PUSH> struct KernelSetup {
     }
 };
 
-template <class Op, bool PUSH> KernelSetup<Op, PUSH>& kernel_setup()
+template <class Op, bool PUSH, bool TS> KernelSetup<Op, PUSH, TS>& kernel_setup()
 {
-    static KernelSetup<Op, PUSH> s;
+    static KernelSetup<Op, PUSH, TS> s;
     return s;
 }
 
@@ -66,6 +66,27 @@ inline void plan_zchunks(int tiles_xy, int nz, int warm, int grid_cap, int* nzc_
     *len_out = (nz + best - 1) / best;
 }
 
+template <class Op, bool PUSH, bool TS>
+int launch_variant(const StreamParams& P, const TensorMaps& M, const OutMaps& OM, int device, int num_sms, cudaStream_t stream,
+                   int tiles_xy, int nz, StreamParams* planned)
+{
+    using G = Geo<Op>;
+    int bps = 0;
+    if (int rc = kernel_setup<Op, PUSH, TS>().get(device, &bps)) return rc;
+    StreamParams Q = P;
+    const int grid_cap = num_sms * bps;
+    plan_zchunks(tiles_xy, nz, Op::WARM, grid_cap, &Q.nzc, &Q.zc_len);
+    const long long items = (long long)tiles_xy * Q.nzc;
+    if (items > 0x7fffffffLL) { set_error("grid too large"); return B200_ERR_ARG; }
+    Q.nitems = (int)items;
+    const int grid = (int)(items < grid_cap ? items : grid_cap);
+    stream_kernel<Op, PUSH, TS><<<grid, G::NTHREADS, G::SMEM_BYTES, stream>>>(Q, M, OM);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+    (void)planned;
+    return B200_OK;
+}
+
 template <class Op> int launch_stream(const HostArgs& a)
 {
     using T = typename Op::real;
@@ -74,11 +95,10 @@ template <class Op> int launch_stream(const HostArgs& a)
     const b200_test_info* ti = b200_get_test_info(d.test);
 
     const bool push = d.push_lo || d.push_hi;
-    int bps = 0;
-    if (int rc = push ? kernel_setup<Op, true>().get(a.device, &bps) : kernel_setup<Op, false>().get(a.device, &bps)) return rc;
 
     StreamParams P{};
     TensorMaps M{};
+    OutMaps OM{};
     P.nx = d.nx; P.ny = d.ny; P.ns = (ti->ndims == 3) ? d.ns : 1;
     P.nxny = (long long)d.nx * d.ny;
     P.xlo = ti->lo[0]; P.xhi = P.nx - ti->hi[0];
@@ -135,40 +155,51 @@ template <class Op> int launch_stream(const HostArgs& a)
 
     P.ntx = (P.nx + Op::TX - 1) / Op::TX;
     P.nty = (P.yhi - P.ylo + Op::TY - 1) / Op::TY;
-    const int grid_cap = a.num_sms * bps;
-    plan_zchunks(P.ntx * P.nty, P.z1 - P.z0, Op::WARM, grid_cap, &P.nzc, &P.zc_len);
-    const long long items = (long long)P.ntx * P.nty * P.nzc;
-    if (items > 0x7fffffffLL) { set_error("grid too large"); return B200_ERR_ARG; }
-    P.nitems = (int)items;
 
     if (P.use_tma) {
         for (int s = 0; s < Op::NSTAGED; s++) {
-            TmaBoxKey key{P.arr[Op::spec(s).slot], P.nx, P.ny, P.ns, (int)sizeof(T), G::bw(s), G::bh(s)};
+            TmaBoxKey key{P.arr[Op::spec(s).slot], P.nx, P.ny, P.ns, (int)sizeof(T), G::bw(s), G::bh(s), 0, 0};
             if (int rc = get_tensor_map(key, &M.m[s])) return rc;
         }
     }
+    // TMA-store output path: tensor maps over the vector-reachable interior of every listed output
+    static const bool no_ts = getenv("B200_NO_TMA_STORE") != nullptr;
+    bool ts = G::TS && P.use_tma && !no_ts && P.nx > 2 * G::V;
+    if (ts) {
+        for (int q = 0; q < G::NOUT; q++) {
+            T* base = reinterpret_cast<T*>(P.arr[Op::out_slot(q)]) + (size_t)P.ylo * P.nx + G::V;
+            TmaBoxKey key{base, P.nx - 2 * G::V, P.yhi - P.ylo, P.ns, (int)sizeof(T), Op::TX, Op::TY, P.nx, P.ny};
+            if (int rc = get_tensor_map(key, &OM.m[q])) return rc;
+            TmaBoxKey key0{base, P.nx - 2 * G::V, P.yhi - P.ylo, P.ns, (int)sizeof(T), Op::TX - G::V, Op::TY, P.nx, P.ny};
+            if (int rc = get_tensor_map(key0, &OM.m0[q])) return rc;
+        }
+    }
 
-    const int grid = (int)(items < grid_cap ? items : grid_cap);
-    if (push) stream_kernel<Op, true><<<grid, G::NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
-    else stream_kernel<Op, false><<<grid, G::NTHREADS, G::SMEM_BYTES, a.stream>>>(P, M);
-    B200_CUDA(cudaGetLastError());
-    count_launch();
-    return B200_OK;
+    const int tiles_xy = P.ntx * P.nty, nz = P.z1 - P.z0;
+    if constexpr (G::TS) {
+        if (ts) {
+            if (push) return launch_variant<Op, true, true>(P, M, OM, a.device, a.num_sms, a.stream, tiles_xy, nz, nullptr);
+            return launch_variant<Op, false, true>(P, M, OM, a.device, a.num_sms, a.stream, tiles_xy, nz, nullptr);
+        }
+    }
+    if (push) return launch_variant<Op, true, false>(P, M, OM, a.device, a.num_sms, a.stream, tiles_xy, nz, nullptr);
+    return launch_variant<Op, false, false>(P, M, OM, a.device, a.num_sms, a.stream, tiles_xy, nz, nullptr);
 }
 
 template <class Op> int info_stream(KernelInfo* ki, const char* name)
 {
     cudaFuncAttributes fa;
-    B200_CUDA(cudaFuncGetAttributes(&fa, stream_kernel<Op, false>));
+    constexpr bool TS = Geo<Op>::TS;
+    B200_CUDA(cudaFuncGetAttributes(&fa, stream_kernel<Op, false, TS>));
     ki->regs = fa.numRegs;
     ki->smem_bytes = Geo<Op>::SMEM_BYTES;
     ki->name = name;
     int dev = 0, bps = 0;
     B200_CUDA(cudaGetDevice(&dev));
-    if (int rc = kernel_setup<Op, false>().get(dev, &bps)) return rc;
+    if (int rc = kernel_setup<Op, false, TS>().get(dev, &bps)) return rc;
     ki->blocks_per_sm = bps;
     int bps_push = 0;      // also prepares the halo-pushing variant (used by multi-GPU launches)
-    if (int rc = kernel_setup<Op, true>().get(dev, &bps_push)) return rc;
+    if (int rc = kernel_setup<Op, true, TS>().get(dev, &bps_push)) return rc;
     return B200_OK;
 }
 

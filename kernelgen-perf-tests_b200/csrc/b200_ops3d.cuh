@@ -21,13 +21,18 @@ namespace b200 {
 // formed and out_{p-1} = acc_{p-1} + beta*C_p is emitted: two live values per point, no queue.
 // (beta is distributed over the z+1 term: a re-association.)
 // ------------------------------------------------------------------------------------------
-template <typename T> struct LaplacianOp {
+template <typename T> struct LaplacianOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
+#ifdef B200_EXP_TS      // experiment build: w1 through the TMA-store path (measured slower, profiles/README.md)
+    static constexpr int NOUT = 1;
+    static constexpr int out_slot(int) { return 1; }
+    static constexpr int out_dpl(int) { return 0; }
+#endif
     using G = Geo<LaplacianOp>;
     static constexpr int V = G::V, CPT = G::CPT;
     struct State { T acc[CPT][V], cp[CPT][V]; };
@@ -70,7 +75,7 @@ template <typename T> struct LaplacianOp {
 //     acc_p      = m0*C_p + inplane_p + m1*C_{p-1} + m2*C_{p-2}
 // rings of two: acc[PH&1] = acc_s, acc[(PH+1)&1] = acc_{s+1}; Cq[PH&1] = C_s, Cq[(PH+1)&1] = C_{s+1}.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct Wave13ptOp {
+template <typename T> struct Wave13ptOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 4, PERIOD = 2;
@@ -125,7 +130,7 @@ template <typename T> struct Wave13ptOp {
 // ring z[2]: z[PH] = uz plane s-1, z[PH^1] = plane s; plane s+1 arrives.
 // u is rewritten every sweep and never read: streamed past the L2.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct DivergenceOp {
+template <typename T> struct DivergenceOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 5, HOLD = 0, WARM = 2, PERIOD = 2;
@@ -175,13 +180,18 @@ template <typename T> struct DivergenceOp {
 // plane) and uz of plane s = gamma*(C_p - C_{s-1}).  ring Cq[2]: Cq[PH&1] = C_{s-1}, Cq[(PH+1)&1] = C_s.
 // The three outputs are rewritten every sweep and never read: streamed past the L2.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct GradientOp {
+template <typename T> struct GradientOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
     static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
+#ifdef B200_EXP_TS      // experiment build: ux, uy (plane s+1) and uz (plane s) through the TMA-store path
+    static constexpr int NOUT = 3;
+    static constexpr int out_slot(int q) { return 1 + q; }
+    static constexpr int out_dpl(int q) { return q < 2 ? 1 : 0; }
+#endif
     using G = Geo<GradientOp>;
     static constexpr int V = G::V, CPT = G::CPT;
     struct State { T Cq[2][CPT][V]; };
@@ -229,7 +239,7 @@ template <typename T> struct GradientOp {
 // The d sum keeps the reference's textual order (it is ill-conditioned); one IEEE division.
 // ring xq[3]: xq[(PH+k)%3] = xz plane s-2+k (k=0..2); plane s+1 arrives and replaces s-2.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct Uxx1Op {
+template <typename T> struct Uxx1Op : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 12 : 6, NC, 128), STAGES = 5, HOLD = 0, WARM = 3, PERIOD = 3;
@@ -302,7 +312,7 @@ template <typename T> struct Uxx1Op {
 //     acc_p      = c0*C_p + c1*F_p + c2*D_p + c3*G_p + c1*C_{p-1} + c2*F_{p-1} + c3*C_{p-2}
 // Five live values per point: rings of two for acc and C, one F.  Re-associated.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct LapgsrbOp {
+template <typename T> struct LapgsrbOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 8, HOLD = 0, WARM = 4, PERIOD = 2;
@@ -370,7 +380,7 @@ template <typename T> B200_DEV void cubic_weights(T t, T (&w)[4])
     w[3] = -sixth * tm1 * t * tp1;
 }
 
-template <typename T> struct TricubicOp {
+template <typename T> struct TricubicOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 12 : 6, NC, 128), STAGES = 6, HOLD = 3, WARM = 3, PERIOD = 1;

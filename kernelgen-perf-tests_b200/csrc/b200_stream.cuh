@@ -85,6 +85,26 @@ struct alignas(64) TensorMaps {
     CUtensorMap m[MAX_STAGED];
 };
 
+// Output side (TMA stores).  An Op that lists its outputs (NOUT > 0) has its results staged in shared
+// memory and written by cp.async.bulk.tensor from a dedicated store warp: whole tiles leave the SM as bulk
+// transactions, the consumer warps never wait on a global store.  The tensor map of an output covers
+// exactly the part of the interior that whole 16-byte vectors can reach -- x in [V, nx-V), rows
+// [ylo, yhi) -- so the boundary shell is protected by the TMA unit's own clipping; the first and last
+// vector of a row (which contain boundary elements) are stored by their threads, element-predicated.
+constexpr int MAX_OUT = 3;
+// (A TMA store must not start at a negative coordinate -- it raises an illegal-instruction error -- so
+// the first x-tile, whose first vector is excluded, uses a second map with a box narrower by V and a
+// staging tile packed accordingly.)
+struct alignas(64) OutMaps {
+    CUtensorMap m[MAX_OUT];        // box TX x TY, x-tiles 1..
+    CUtensorMap m0[MAX_OUT];       // box (TX - V) x TY, x-tile 0
+};
+struct NoTmaStore {                       // base of the Ops that keep the register store path
+    static constexpr int NOUT = 0;
+    static constexpr int out_slot(int) { return -1; }
+    static constexpr int out_dpl(int) { return 0; }
+};
+
 constexpr int round_up_c(int a, int b) { return (a + b - 1) / b * b; }
 
 // Compile-time geometry of an Op.
@@ -95,7 +115,7 @@ template <class Op> struct Geo {
     static constexpr int TY = Op::TY;
     static constexpr int LX = TX / V;            // threads along x
     static constexpr int NC = Op::NC;            // consumer threads
-    static constexpr int NTHREADS = NC + 32;     // + the producer warp
+    static constexpr int NTHREADS = NC + 32 + (Op::NOUT > 0 ? 32 : 0);     // + the producer warp (+ the store warp)
     static constexpr int LY = NC / LX;           // thread rows
     static constexpr int CPT = TY / LY;          // rows ("columns" in z) per thread
     static_assert((NC == 384 || NC == 512) && TX % V == 0 && NC % LX == 0 && TY % LY == 0, "bad tile");
@@ -111,7 +131,30 @@ template <class Op> struct Geo {
         return o;
     }
     static constexpr int STAGE_BYTES = arr_off(Op::NSTAGED);
-    static constexpr int SMEM_BYTES = 128 /*mbarriers*/ + 128 /*alignment slack*/ + Op::STAGES * STAGE_BYTES;
+    static constexpr int NOUT = Op::NOUT;
+    static constexpr bool TS = NOUT > 0;                                 // TMA-store output path
+    static constexpr int OB = 2;                                         // output staging buffers
+    static constexpr int OUT_TILE_BYTES = TX * TY * (int)sizeof(T);
+    static constexpr int OUT_BYTES = NOUT * OUT_TILE_BYTES;              // one staging buffer: NOUT tiles
+    static constexpr int HDR_BYTES = 256;                                // mbarriers
+    static constexpr int RING_BYTES = Op::STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = HDR_BYTES + 128 /*alignment slack*/ + RING_BYTES + OB * OUT_BYTES;
+    static_assert(SMEM_BYTES <= 232448, "tile does not fit the 227 KB of shared memory");
+    static_assert(NOUT <= MAX_OUT && OUT_TILE_BYTES % 128 == 0, "bad output tile");
+    // ordinal of output slot SLOT among the Op's TMA-stored outputs
+    static constexpr int out_q(int slot)
+    {
+        for (int q = 0; q < NOUT; q++)
+            if (Op::out_slot(q) == slot) return q;
+        return -1;
+    }
+    // does the step of output plane s store anything?  (output q goes to plane s + out_dpl(q))
+    static constexpr bool emits(int s, int za, int zb)
+    {
+        for (int q = 0; q < NOUT; q++)
+            if (s + Op::out_dpl(q) >= za && s + Op::out_dpl(q) < zb) return true;
+        return false;
+    }
     static_assert(Op::STAGES <= MAX_STAGES && Op::NSTAGED <= MAX_STAGED, "too many stages");
     static_assert(Op::STAGES > Op::HOLD, "ring too shallow");
 };
@@ -120,12 +163,14 @@ template <class Op> struct Geo {
 // there: a store is a row test, one multiply-add for the 32-bit element offset and one 64-bit
 // address add off a warp-uniform plane pointer.  PUSH = this launch also stores halo planes into
 // a neighbour GPU's memory; single-GPU launches are compiled without that code.
-template <class Op, bool PUSH> struct Ctx {
+template <class Op, bool PUSH, bool TS = false> struct Ctx {
     using T = typename Op::real;
     using G = Geo<Op>;
     static constexpr int V = G::V;
     const StreamParams& P;
     unsigned char* stages;      // base of the ring
+    unsigned char* ostage;      // TS: output staging buffer of this step
+    int opitch, oshift;         // TS, per item: row pitch of the staging tile and the column it starts at (x-tile 0: TX-V, V)
     uint32_t st;                // ring stage of this step
     int X0, Y0;                 // global x of tile column 0, global y of tile row 0
     int s;                      // output plane of this step
@@ -149,6 +194,10 @@ template <class Op, bool PUSH> struct Ctx {
         xmode = (all && P.vec_ok) ? 1 : (some ? 2 : 0);
         rows_valid = min(G::TY, P.yhi - Y0);
         idx0 = (unsigned)(Y0 * P.nx + x);
+        if constexpr (TS) {
+            oshift = X0 == 0 ? V : 0;
+            opitch = G::TX - oshift;
+        }
     }
 
     // Pointer to this thread's 16-byte vector in tile row `row` (tile-local output row, may be
@@ -196,7 +245,20 @@ template <class Op, bool PUSH> struct Ctx {
     {
         if (row >= rows_valid || xmode == 0) return;
         const unsigned off = idx0 + (unsigned)(row * P.nx);
-        put(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val);
+        if constexpr (TS && G::out_q(SLOT) >= 0) {
+            if (xmode == 1) {
+                // whole vector inside the interior: into the staging tile, the store warp sends it with TMA
+                VReg<T> r;
+#pragma unroll
+                for (int v = 0; v < V; v++) r[v] = val[v];
+                T* dst = reinterpret_cast<T*>(ostage + G::out_q(SLOT) * G::OUT_TILE_BYTES) + (row * opitch + V * tx - oshift);
+                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(r.v);
+            } else {
+                put(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val);
+            }
+        } else {
+            put(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val);
+        }
         if constexpr (PUSH) {
             // fused halo push: the same values also go to the neighbour GPU's ghost planes (rows for
             // the 2D tests) through a peer-mapped pointer, i.e. over NVLink, while the sweep runs
@@ -304,9 +366,9 @@ template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int i
 // (measured: profiles/README.md).
 template <class Op> struct RegCap { static constexpr int value = Op::NC == 512 ? 96 : 128; };
 
-template <class Op, bool PUSH>
+template <class Op, bool PUSH, bool TS>
 __global__ void __launch_bounds__(Geo<Op>::NTHREADS) __maxnreg__(RegCap<Op>::value)
-stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ TensorMaps M)
+stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ TensorMaps M, const __grid_constant__ OutMaps OM)
 {
     using G = Geo<Op>;
     constexpr int S = Op::STAGES;
@@ -314,7 +376,10 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
     unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + S;
-    unsigned char* stages = smem + 128;
+    uint64_t* ofull = full + 2 * MAX_STAGES;       // [OB] staging buffer written by all consumer warps
+    uint64_t* oempty = ofull + G::OB;              // [OB] staging buffer read out by the TMA store
+    unsigned char* stages = smem + G::HDR_BYTES;
+    unsigned char* ostages = stages + G::RING_BYTES;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -324,6 +389,13 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
         for (int i = 0; i < S; i++) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], G::NC / 32);
+        }
+        if constexpr (TS) {
+#pragma unroll
+            for (int i = 0; i < G::OB; i++) {
+                mbar_init(&ofull[i], G::NC / 32);
+                mbar_init(&oempty[i], 1);
+            }
         }
         mbar_fence_init();
         if constexpr (PUSH) {
@@ -374,13 +446,39 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
                 }
             }
         }
+    } else if (warp == G::NC / 32 + 1) {
+        // ------------------------------ store warp (TMA stores) ------------------------------
+        if constexpr (TS) {
+            if (lane != 0) goto finish;
+            uint32_t og = 0;
+            for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
+                const ItemCoords c = decode_item<Op>(P, item);
+                for (int s = c.za - Op::WARM; s < c.zb; ++s) {
+                    if (!G::emits(s, c.za, c.zb)) continue;
+                    const uint32_t ob = og & 1u;
+                    mbar_wait(&ofull[ob], (og >> 1) & 1u);
+#pragma unroll
+                    for (int q = 0; q < G::NOUT; q++) {
+                        const int p = s + Op::out_dpl(q);
+                        if (p >= c.za && p < c.zb)
+                            tma_store_3d(c.X0 == 0 ? &OM.m0[q] : &OM.m[q], ostages + ob * G::OUT_BYTES + q * G::OUT_TILE_BYTES,
+                                         c.X0 == 0 ? 0 : c.X0 - G::V, c.Y0 - P.ylo, p);
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read<1>();              // the previous group has been read out of its buffer
+                    if (og >= 1u) mbar_arrive(&oempty[ob ^ 1u]);
+                    ++og;
+                }
+            }
+            tma_store_wait_all();
+        }
     } else {
         // ------------------------------ consumer warps ------------------------------
         Op op(P);
         typename Op::State state;
-        Ctx<Op, PUSH> ctx{P, stages, 0u, 0, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0, 0u, 0ll};
+        Ctx<Op, PUSH, TS> ctx{P, stages, ostages, G::TX, 0, 0u, 0, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0, 0u, 0ll};
         uint32_t st = 0, ph = 0, rel_st = (uint32_t)(S - Op::HOLD) % S;    // ring stage / parity of this step; stage to hand back
-        uint32_t g = 0;
+        uint32_t g = 0, og = 0;
         for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
             const ItemCoords c = decode_item<Op>(P, item);
             ctx.begin_item(c.X0, c.Y0);
@@ -392,8 +490,25 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
                 ctx.rel = s - c.za;
                 ctx.poff = (long long)s * P.nxny;
                 op.pre(ctx, state);
+                bool emit = false;
+                if constexpr (TS) {
+                    emit = G::emits(s, c.za, c.zb);
+                    if (emit) {
+                        // the staging buffer of two emitting steps ago must have left through the TMA store
+                        mbar_wait(&oempty[og & 1u], ((og >> 1) & 1u) ^ 1u);
+                        ctx.ostage = ostages + (og & 1u) * G::OUT_BYTES;
+                    }
+                }
                 mbar_wait(&full[st], ph);
-                step_dispatch<Op, Ctx<Op, PUSH>>(op, ctx, state, phase);
+                step_dispatch<Op, Ctx<Op, PUSH, TS>>(op, ctx, state, phase);
+                if constexpr (TS) {
+                    if (emit) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ofull[og & 1u]);
+                        ++og;
+                    }
+                }
                 if (local >= Op::HOLD) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[rel_st]);

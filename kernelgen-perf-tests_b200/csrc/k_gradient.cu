@@ -66,13 +66,18 @@ template <typename T> static int launch_fanout(const HostArgs& a, int mode)
 
 // modes 4 / 5: the engine itself (TMA ring, 12 consumer warps, Ctx::store) doing a point-wise copy of u into
 // ux, uy, uz -- without (4) / with (5) gradient's halo'd tile: the engine's ceiling for 1 read + 3 writes
-template <typename T, int HALO> struct EngineFanoutOp {
+template <typename T, int HALO> struct EngineFanoutOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 0, PERIOD = 1;
     static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, HALO, HALO, HALO, 0, 0}; }
+#ifdef B200_EXP_TS
+    static constexpr int NOUT = 3;
+    static constexpr int out_slot(int q) { return 1 + q; }
+    static constexpr int out_dpl(int) { return 0; }
+#endif
     using G = Geo<EngineFanoutOp>;
     static constexpr int V = G::V, CPT = G::CPT;
     struct State { };
@@ -94,9 +99,11 @@ template <typename T, int HALO> struct EngineFanoutOp {
     }
 };
 
+int launch_tma_copy(int dtype, const HostArgs& a, int nout);
 int launch_gradient(int dtype, const HostArgs& a)
 {
     static const int dbg = getenv("B200_DEBUG_FANOUT") ? atoi(getenv("B200_DEBUG_FANOUT")) : 0;
+    if (dbg == 6) return launch_tma_copy(dtype, a, 3);
     if (dbg == 4) return dtype == B200_F32 ? launch_stream<EngineFanoutOp<float, 0>>(a) : launch_stream<EngineFanoutOp<double, 0>>(a);
     if (dbg == 5) return dtype == B200_F32 ? launch_stream<EngineFanoutOp<float, 1>>(a) : launch_stream<EngineFanoutOp<double, 1>>(a);
     if (dbg) return dtype == B200_F32 ? launch_fanout<float>(a, dbg) : launch_fanout<double>(a, dbg);

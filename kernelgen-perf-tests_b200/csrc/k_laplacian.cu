@@ -25,13 +25,18 @@ int info_laplacian(int dtype, KernelInfo* ki)
 // tools/gap_probe.py.  B200_DEBUG_COPY=2: same with the laplacian's halo'd tile (loads the halos,
 // ignores them).
 namespace b200 {
-template <typename T, int HALO> struct EngineCopyOp {
+template <typename T, int HALO> struct EngineCopyOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 0, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, HALO, HALO, HALO, 0, 0}; }
+#ifdef B200_EXP_TS
+    static constexpr int NOUT = 1;
+    static constexpr int out_slot(int) { return 1; }
+    static constexpr int out_dpl(int) { return 0; }
+#endif
     using G = Geo<EngineCopyOp>;
     static constexpr int V = G::V, CPT = G::CPT;
     struct State { };
@@ -50,8 +55,84 @@ template <typename T, int HALO> struct EngineCopyOp {
         }
     }
 };
+// B200_DEBUG_COPY=3 / 4: no consumers at all -- a pure TMA copy (global -> shared ring -> global, one loading and
+// one storing thread per CTA, persistent grid, the engine's item order) of w0 into w1 (3) or of u into 3 arrays
+// (4, via the gradient entry point).  Box = B200_TC_TX x B200_TC_TY elements.  The ceiling of a TMA-store path.
+__global__ void __launch_bounds__(64) tma_copy_kernel(const __grid_constant__ CUtensorMap in, const __grid_constant__ TensorMaps out,
+                                                       int nout, int tx, int ty, int ntx, int nty, int nz, int zc, int stage_bytes, int S)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + 8;
+    unsigned char* stages = smem + 128;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int nzc = (nz + zc - 1) / zc, nitems = ntx * nty * nzc;
+    if (threadIdx.x == 0) {
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int c = item / (ntx * nty), t = item - c * ntx * nty, yi = t / ntx, xi = t - yi * ntx;
+            for (int z = c * zc; z < min(nz, c * zc + zc); z++, g++) {
+                const uint32_t st = g % S, ph = (g / S) & 1u;
+                mbar_wait(&empty[st], ph ^ 1u);
+                mbar_arrive_expect_tx(&full[st], (uint32_t)stage_bytes);
+                tma_load_3d(stages + st * stage_bytes, &in, &full[st], xi * tx, yi * ty, z);
+            }
+        }
+    } else if (threadIdx.x == 32) {
+        constexpr int K = 2;                       // stores in flight
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int c = item / (ntx * nty), t = item - c * ntx * nty, yi = t / ntx, xi = t - yi * ntx;
+            for (int z = c * zc; z < min(nz, c * zc + zc); z++, g++) {
+                const uint32_t st = g % S, ph = (g / S) & 1u;
+                mbar_wait(&full[st], ph);
+                for (int q = 0; q < nout; q++)
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&out.m[q])), "r"(smem_u32(stages + st * stage_bytes)),
+                                   "r"(xi * tx), "r"(yi * ty), "r"(z) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(K) : "memory");
+                if (g >= (uint32_t)K) mbar_arrive(&empty[(g - K) % S]);
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+int launch_tma_copy(int dtype, const HostArgs& a, int nout)
+{
+    const b200_sweep_desc& d = *a.desc;
+    const int esz = dtype == B200_F32 ? 4 : 8;
+    const int tx = getenv("B200_TC_TX") ? atoi(getenv("B200_TC_TX")) : 128;
+    const int ty = getenv("B200_TC_TY") ? atoi(getenv("B200_TC_TY")) : 24;
+    const int S = getenv("B200_TC_S") ? atoi(getenv("B200_TC_S")) : 6;
+    const int zc = getenv("B200_TC_ZC") ? atoi(getenv("B200_TC_ZC")) : 32;
+    CUtensorMap in;
+    TensorMaps out{};
+    TmaBoxKey key{a.arrays[0], d.nx, d.ny, d.ns, esz, tx, ty};
+    if (int rc = get_tensor_map(key, &in)) return rc;
+    for (int q = 0; q < nout; q++) {
+        TmaBoxKey ko{a.arrays[1 + q], d.nx, d.ny, d.ns, esz, tx, ty};
+        if (int rc = get_tensor_map(ko, &out.m[q])) return rc;
+    }
+    const int stage_bytes = (tx * ty * esz + 127) / 128 * 128;
+    const int smem = 256 + S * stage_bytes;
+    B200_CUDA(cudaFuncSetAttribute(tma_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tma_copy_kernel<<<a.num_sms, 64, smem, a.stream>>>(in, out, nout, tx, ty, (d.nx + tx - 1) / tx, (d.ny + ty - 1) / ty, d.ns, zc,
+                                                       tx * ty * esz, S);
+    B200_CUDA(cudaGetLastError());
+    count_launch();
+    return B200_OK;
+}
+
 int launch_debug_copy(int dtype, const HostArgs& a, int mode)
 {
+    if (mode == 3) return launch_tma_copy(dtype, a, 1);
     if (mode == 2) return dtype == B200_F32 ? launch_stream<EngineCopyOp<float, 1>>(a) : launch_stream<EngineCopyOp<double, 1>>(a);
     return dtype == B200_F32 ? launch_stream<EngineCopyOp<float, 0>>(a) : launch_stream<EngineCopyOp<double, 0>>(a);
 }
