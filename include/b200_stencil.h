@@ -174,6 +174,15 @@ int b200_plan(b200_ctx* ctx, int test, int dtype, int nx, int ny, int ns,
               const double* scalars, int nscalars);
 int b200_alloc(b200_ctx* ctx);
 int b200_load(b200_ctx* ctx, int slot, const void* host);
+/* Arrays whose interior the first sweep overwrites before anything reads it (the output buffers:
+ * laplacian w1, wave13pt w2, divergence u, gradient ux/uy/uz, ... -- b200_slot_interior_dead)
+ * only need their boundary shell on the device: the reference's cuda target copies them whole
+ * (laplacian/laplacian.c:257-258), the sweeps never touch the shell, the result keeps it.
+ * b200_load_shell copies exactly the points outside the interior box (a few strided copies), so
+ * "data load time" shrinks by one array (laplacian: 2 -> 1, gradient: 4 -> 1).  Only valid when
+ * at least one sweep follows (with nt = 0 the reference reports the untouched array). */
+int b200_slot_interior_dead(int test, int slot);
+int b200_load_shell(b200_ctx* ctx, int slot, const void* host);
 int b200_run(b200_ctx* ctx, int niters, b200_stats* stats);
 int b200_result_slot(const b200_ctx* ctx);          /* slot (original numbering) the reference reports f_mean on */
 int b200_save(b200_ctx* ctx, int slot, void* host);

@@ -29,7 +29,7 @@ MAX_ARRAYS, MAX_SCALARS = 8, 8
 EXPORTS = ["b200_get_test_info", "b200_test_by_name", "b200_last_error", "b200_api_version",
            "b200_interior_points", "b200_device_count", "b200_sweep", "b200_sweep_loop", "b200_slab_loop", "b200_kernel_info",
            "b200_launch_count", "b200_init", "b200_plan", "b200_alloc", "b200_load", "b200_run",
-           "b200_result_slot", "b200_save", "b200_free", "b200_destroy", "b200_host_alloc",
+           "b200_slot_interior_dead", "b200_load_shell", "b200_result_slot", "b200_save", "b200_free", "b200_destroy", "b200_host_alloc",
            "b200_host_free", "b200_device_alloc", "b200_device_free", "b200_ipc_export",
            "b200_ipc_import", "b200_ipc_close", "b200_signal", "b200_wait"]
 IPC_HANDLE_BYTES = 64
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     L.b200_plan.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.POINTER(C.c_double), C.c_int]
     L.b200_alloc.argtypes = [C.c_void_p]
     L.b200_load.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.b200_load_shell.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.b200_slot_interior_dead.argtypes = [C.c_int, C.c_int]
     L.b200_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(Stats)]
     L.b200_result_slot.argtypes = [C.c_void_p]
     L.b200_save.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -276,6 +278,14 @@ class Context:
         assert host.flags.c_contiguous and host.dtype == NP_DTYPE[self.dtype]
         _check(load().b200_load(self.h, slot, host.ctypes.data_as(C.c_void_p)))
 
+    def load_array_shell(self, slot: int, host: np.ndarray):
+        """Boundary shell only (b200_load_shell): for the arrays the first sweep overwrites."""
+        assert host.flags.c_contiguous and host.dtype == NP_DTYPE[self.dtype]
+        _check(load().b200_load_shell(self.h, slot, host.ctypes.data_as(C.c_void_p)))
+
+    def interior_dead(self, slot: int) -> bool:
+        return bool(load().b200_slot_interior_dead(self.test, slot))
+
     def run(self, niters: int) -> dict:
         st = Stats()
         _check(load().b200_run(self.h, niters, C.byref(st)))
@@ -299,12 +309,16 @@ class Context:
             self.h = C.c_void_p()
 
     # convenience: the whole driver loop on host arrays (in slot order); arrays are updated in place
-    def run_on_host_arrays(self, test, dtype, nx, ny, ns, scalars, arrays, niters) -> tuple[int, dict]:
+    def run_on_host_arrays(self, test, dtype, nx, ny, ns, scalars, arrays, niters, shell_loads=True) -> tuple[int, dict]:
         self.plan(test, dtype, nx, ny, ns, scalars)
         self.alloc()
         try:
             for q, a in enumerate(arrays):
-                self.load_array(q, a)
+                # like the C drivers: output buffers only need their shell when a sweep follows
+                if niters >= 1 and shell_loads and self.interior_dead(q):
+                    self.load_array_shell(q, a)
+                else:
+                    self.load_array(q, a)
             stats = self.run(niters)
             slot = self.result_slot()
             for q, a in enumerate(arrays):

@@ -206,8 +206,16 @@ int main(int argc, char* argv[])
 	size_t loaded = 0;
 	for (int q = 0; q < na; q++)
 	{
-		B200_SAFE_CALL(b200_load(ctx, q, a[q]));
-		loaded += len[q] * sizeof(real);
+		/* output buffers: the first sweep overwrites their interior before anything reads it, so
+		 * only the boundary shell has to travel (the reference's cuda target copies them whole,
+		 * laplacian.c:257-258); with nt = 0 the untouched array is the result, so it goes whole */
+		if (nt >= 1 && b200_slot_interior_dead(TEST, q))
+			B200_SAFE_CALL(b200_load_shell(ctx, q, a[q]));
+		else
+		{
+			B200_SAFE_CALL(b200_load(ctx, q, a[q]));
+			loaded += len[q] * sizeof(real);
+		}
 	}
 	get_time(&t1);
 	double load_t = get_time_diff((struct timespec*)&t0, (struct timespec*)&t1);

@@ -28,10 +28,12 @@ SCAL = {"laplacian": [0.3, 0.1], "wave13pt": [0.6, -0.03, 0.09], "lapgsrb": [0.5
 
 
 @pytest.mark.parametrize("g", [2, 3, 4, 8])
-def test_context_slabs_bitwise(pkg, oracle, g):
-    """Single process, g GPUs (what B200_NGPUS=g does in the C drivers): peer-pointer halo push."""
+def test_context_slabs_bitwise(pkg, oracle, g, monkeypatch):
+    """Single process, g GPUs (what B200_NGPUS=g does in the C drivers): peer-pointer halo push.
+    Buffers start NaN-poisoned and output arrays are loaded shell-only, as the drivers do."""
     if ngpus() < g:
         pytest.skip(f"needs {g} GPUs")
+    monkeypatch.setenv("B200_POISON", "1")
     one, many = pkg.Context(1), pkg.Context(g)
     try:
         for real in ("double", "float"):

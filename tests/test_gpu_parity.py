@@ -166,6 +166,31 @@ def test_matmul_1024_float_accuracy(ctx):
     assert ed <= 1e-14, ed
 
 
+@pytest.mark.parametrize("test", STENCILS)
+def test_shell_only_loads_poisoned(pkg, oracle, oracle_strict, test, monkeypatch):
+    """b200_load_shell: output buffers receive only their boundary shell.  Device buffers start as NaN
+    patterns (B200_POISON), so a missed shell point or an unwritten interior point cannot hide; result
+    must equal the run with whole-array loads bit for bit, and the oracle within the bar."""
+    monkeypatch.setenv("B200_POISON", "1")
+    info = oracle.info(test)
+    c = pkg.Context(1)
+    try:
+        for real in ("double", "float"):
+            for nx, ny, ns in ([(132, 21, 13), (64, 9, 7), (5, 5, 5)] if info["ndims"] == 3 else [(132, 75, 1), (8, 9, 1)]):
+                scalars, inputs, _ = oracle.init(test, real, nx, ny, ns)
+                a = [x.copy() for x in inputs]
+                b = [x.copy() for x in inputs]
+                c.run_on_host_arrays(test, real, nx, ny, ns, scalars, a, 3, shell_loads=True)
+                c.run_on_host_arrays(test, real, nx, ny, ns, scalars, b, 3, shell_loads=False)
+                for q in range(len(a)):
+                    assert np.array_equal(a[q], b[q]), f"{test}/{real} {nx}x{ny}x{ns}: slot {q} differs with shell-only loads"
+                want = [x.copy() for x in inputs]
+                (oracle_strict if test == "gameoflife" else oracle).run(test, real, nx, ny, ns, 3, scalars, want)
+                check(test, real, nx, ny, ns, 3, scalars, inputs, a, want)
+    finally:
+        c.destroy()
+
+
 def test_degenerate_and_errors(ctx, pkg):
     a = [np.ones(27), np.ones(27) * 2]
     slot, got, _ = gpu_run(ctx, "wave13pt", "double", 3, 3, 3, 2, [0.1, 0.2, 0.3], a + [np.ones(27) * 3])
