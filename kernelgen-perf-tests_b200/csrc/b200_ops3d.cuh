@@ -78,7 +78,11 @@ template <typename T> struct LaplacianOp : NoTmaStore {
 template <typename T> struct Wave13ptOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
+#ifdef B200_EXP_WAVE_TY18
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 36 : 18, NC, 128), STAGES = 5, HOLD = 0, WARM = 4, PERIOD = 2;
+#else
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 4, PERIOD = 2;
+#endif
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 2;
     static constexpr StagedSpec spec(int a)

@@ -25,13 +25,13 @@ int info_laplacian(int dtype, KernelInfo* ki)
 // tools/gap_probe.py.  B200_DEBUG_COPY=2: same with the laplacian's halo'd tile (loads the halos,
 // ignores them).
 namespace b200 {
-template <typename T, int HALO> struct EngineCopyOp : NoTmaStore {
+template <typename T, int HX, int HY, int TXV, int TYD, int STG> struct EngineCopyOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 0, PERIOD = 1;
+    static constexpr int TX = TXV, TY = pick_ty<T>(sizeof(T) == 4 ? 2 * TYD : TYD, NC, TXV), STAGES = STG, HOLD = 0, WARM = 0, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
-    static constexpr StagedSpec spec(int) { return StagedSpec{0, HALO, HALO, HALO, 0, 0}; }
+    static constexpr StagedSpec spec(int) { return StagedSpec{0, HX ? 1 : 0, HY, HY, 0, 0}; }
 #ifdef B200_EXP_TS
     static constexpr int NOUT = 1;
     static constexpr int out_slot(int) { return 1; }
@@ -55,6 +55,11 @@ template <typename T, int HALO> struct EngineCopyOp : NoTmaStore {
         }
     }
 };
+template <int HX, int HY, int TXV, int TYD, int STG> static int launch_copy_variant(int dtype, const HostArgs& a)
+{
+    return dtype == B200_F32 ? launch_stream<EngineCopyOp<float, HX, HY, TXV, TYD, STG>>(a)
+                             : launch_stream<EngineCopyOp<double, HX, HY, TXV, TYD, STG>>(a);
+}
 // B200_DEBUG_COPY=3 / 4: no consumers at all -- a pure TMA copy (global -> shared ring -> global, one loading and
 // one storing thread per CTA, persistent grid, the engine's item order) of w0 into w1 (3) or of u into 3 arrays
 // (4, via the gradient entry point).  Box = B200_TC_TX x B200_TC_TY elements.  The ceiling of a TMA-store path.
@@ -133,7 +138,18 @@ int launch_tma_copy(int dtype, const HostArgs& a, int nout)
 int launch_debug_copy(int dtype, const HostArgs& a, int mode)
 {
     if (mode == 3) return launch_tma_copy(dtype, a, 1);
-    if (mode == 2) return dtype == B200_F32 ? launch_stream<EngineCopyOp<float, 1>>(a) : launch_stream<EngineCopyOp<double, 1>>(a);
-    return dtype == B200_F32 ? launch_stream<EngineCopyOp<float, 0>>(a) : launch_stream<EngineCopyOp<double, 0>>(a);
+    switch (mode) {         // tile-shape / halo study (tools/quick.sh, profiles/README.md)
+    case 10: return launch_copy_variant<0, 1, 128, 24, 6>(dtype, a);    // y halo only
+    case 11: return launch_copy_variant<1, 0, 128, 24, 6>(dtype, a);    // x halo only
+    case 12: return launch_copy_variant<1, 1, 128, 48, 4>(dtype, a);    // taller tile
+    case 13: return launch_copy_variant<1, 1, 64, 48, 6>(dtype, a);     // narrower, taller
+    case 14: return launch_copy_variant<1, 2, 128, 12, 6>(dtype, a);    // wave13pt / lapgsrb geometry
+    case 15: return launch_copy_variant<1, 2, 64, 24, 6>(dtype, a);     // same point count, squarer
+    case 16: return launch_copy_variant<1, 2, 128, 24, 4>(dtype, a);    // radius 2, taller
+    case 17: return launch_copy_variant<1, 1, 128, 24, 4>(dtype, a);    // shallower ring
+    default: break;
+    }
+    if (mode == 2) return launch_copy_variant<1, 1, 128, 24, 6>(dtype, a);
+    return launch_copy_variant<0, 0, 128, 24, 6>(dtype, a);
 }
 }  // namespace b200

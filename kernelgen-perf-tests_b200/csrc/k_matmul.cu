@@ -42,7 +42,12 @@ template <int BYTES> B200_DEV void cp_async_zfill(void* smem_dst, const void* gs
 B200_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> B200_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int MM_BM = 128, MM_BN = 128, MM_BK = 16, MM_STAGES = 4;
+constexpr int MM_BM = 128, MM_BN = 128;
+#ifndef B200_MM_BK
+#define B200_MM_BK 32
+#endif
+constexpr int MM_BK = B200_MM_BK;                 // k extent of a stage (one __syncthreads per stage)
+template <typename T> constexpr int mm_stages() { return MM_BK == 32 ? (sizeof(T) == 8 ? 3 : 4) : 4; }
 
 template <typename T> struct MmGeo {
     // pitches (in elements): A tile [BK][LDA] (m contiguous), B tile [BN][LDB] (k contiguous)
@@ -52,7 +57,8 @@ template <typename T> struct MmGeo {
     static constexpr int LDB = MM_BK + 4;
     static constexpr int A_ELEMS = MM_BK * LDA, B_ELEMS = MM_BN * LDB;
     static constexpr int STAGE_BYTES = (A_ELEMS + B_ELEMS) * (int)sizeof(T);
-    static constexpr int SMEM_BYTES = MM_STAGES * STAGE_BYTES;
+    static constexpr int STAGES = mm_stages<T>();
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES;
     static constexpr int THREADS = sizeof(T) == 8 ? 512 : 256;
 };
 
@@ -127,7 +133,7 @@ matmul_f64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, co
 
         __syncthreads();                            // the previous tile's readers are done with the ring
 #pragma unroll
-        for (int s = 0; s < MM_STAGES - 1; s++) {
+        for (int s = 0; s < G::STAGES - 1; s++) {
             if (s < nk) {
                 double* st = smem + (size_t)s * (G::A_ELEMS + G::B_ELEMS);
                 mm_load_stage<double, VE>(st, st + G::A_ELEMS, A, B, M, N, K, lda, ldb, m0, n0, s * MM_BK, tid);
@@ -135,17 +141,17 @@ matmul_f64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, co
             cp_async_commit();
         }
         for (int kt = 0; kt < nk; kt++) {
-            cp_async_wait<MM_STAGES - 2>();
+            cp_async_wait<G::STAGES - 2>();
             __syncthreads();
             {
-                const int kn = kt + MM_STAGES - 1;
+                const int kn = kt + G::STAGES - 1;
                 if (kn < nk) {
-                    double* st = smem + (size_t)(kn % MM_STAGES) * (G::A_ELEMS + G::B_ELEMS);
+                    double* st = smem + (size_t)(kn % G::STAGES) * (G::A_ELEMS + G::B_ELEMS);
                     mm_load_stage<double, VE>(st, st + G::A_ELEMS, A, B, M, N, K, lda, ldb, m0, n0, kn * MM_BK, tid);
                 }
                 cp_async_commit();
             }
-            const double* As = smem + (size_t)(kt % MM_STAGES) * (G::A_ELEMS + G::B_ELEMS);
+            const double* As = smem + (size_t)(kt % G::STAGES) * (G::A_ELEMS + G::B_ELEMS);
             const double* Bs = As + G::A_ELEMS;
 #pragma unroll
             for (int ks = 0; ks < MM_BK; ks += 4) {
@@ -226,7 +232,7 @@ matmul_f32_kernel(int M, int N, int K, const float* __restrict__ A, int lda, con
 
         __syncthreads();
 #pragma unroll
-        for (int s = 0; s < MM_STAGES - 1; s++) {
+        for (int s = 0; s < G::STAGES - 1; s++) {
             if (s < nk) {
                 float* st = smem + (size_t)s * (G::A_ELEMS + G::B_ELEMS);
                 mm_load_stage<float, VE>(st, st + G::A_ELEMS, A, B, M, N, K, lda, ldb, m0, n0, s * MM_BK, tid);
@@ -234,17 +240,17 @@ matmul_f32_kernel(int M, int N, int K, const float* __restrict__ A, int lda, con
             cp_async_commit();
         }
         for (int kt = 0; kt < nk; kt++) {
-            cp_async_wait<MM_STAGES - 2>();
+            cp_async_wait<G::STAGES - 2>();
             __syncthreads();
             {
-                const int kn = kt + MM_STAGES - 1;
+                const int kn = kt + G::STAGES - 1;
                 if (kn < nk) {
-                    float* st = smem + (size_t)(kn % MM_STAGES) * (G::A_ELEMS + G::B_ELEMS);
+                    float* st = smem + (size_t)(kn % G::STAGES) * (G::A_ELEMS + G::B_ELEMS);
                     mm_load_stage<float, VE>(st, st + G::A_ELEMS, A, B, M, N, K, lda, ldb, m0, n0, kn * MM_BK, tid);
                 }
                 cp_async_commit();
             }
-            const float* As = smem + (size_t)(kt % MM_STAGES) * (G::A_ELEMS + G::B_ELEMS);
+            const float* As = smem + (size_t)(kt % G::STAGES) * (G::A_ELEMS + G::B_ELEMS);
             const float* Bs = As + G::A_ELEMS;
             // The tensor core truncates when it adds into its FP32 accumulator, a bias that grows with the
             // length of the chain (measured: 6e-5 normwise at K = 8192).  So a stage accumulates from zero in

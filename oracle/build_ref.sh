@@ -57,6 +57,25 @@ for r in float double; do
         -DKGREF_SHIM_SFX=$s "$HERE/ref_shims.c" "$HERE/kgo.c" -o "$OUT/bin/jacobi_${r}" -lrt -lm
 done
 
+# the reference's own naive CUDA target (<test>/cuda/makefile:36-49), rebuilt for sm_100: the GPU-vs-GPU
+# baseline ("the recompiled kernels") that tools/ref_cuda_table.py times beside the b200 kernels
+if command -v nvcc >/dev/null 2>&1; then
+    mkdir -p "$OUT/cuda_bin" "$OUT/obj_cuda"
+    for t in $CTESTS; do
+        [ -d "$REF/$t/cuda" ] || continue
+        for r in float double; do
+            o="$OUT/obj_cuda/${t}_${r}"
+            ( nvcc -w -I"$REF/$t/cuda" -I"$REF/$t" -O3 -arch=sm_100 -Dreal=$r -c "$REF/$t/$t.cu" -o "$o.o" &&
+              nvcc -w -I"$REF/$t/cuda" -I"$REF/$t" -O3 -arch=sm_100 -c "$REF/$t/cuda/cuda_profiling.cu" -o "$o.prof.o" &&
+              nvcc -w -O3 -arch=sm_100 -x c -c "$REF/$t/timing.c" -o "$o.timing.o" &&
+              nvcc -arch=sm_100 "$o.o" "$o.timing.o" "$o.prof.o" -o "$OUT/cuda_bin/${t}_${r}" -lrt \
+                  -Xlinker --wrap=cudaLaunch -Xlinker --wrap=cudaLaunchKernel -Xcompiler -rdynamic --cudart=shared -ldl &&
+              cp "$REF/$t/cuda/kernel" "$OUT/cuda_bin/${t}.kernel" ) 2>/dev/null || echo "reference cuda target of $t ($r) does not build"
+        done
+    done
+    echo "built $OUT/cuda_bin"
+fi
+
 grep -m1 '^flags' /proc/cpuinfo | cut -d: -f2 > "$OUT/build_host_flags.txt"
 rm -rf "$OUT/obj"
 echo "oracle/_ref complete"

@@ -6,7 +6,7 @@
 #   bench_<tag>.json          the bench line itself (NOT under a profiler)
 tag=${1:-r1}
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err
+timeout 1500 python bench.py > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 30 -c 400 --csv \
     --log-file gpurun_out/launches_${tag}.csv python bench.py --steps 20 --warmup 3 --suite none --no-cpu > /dev/null 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none \
