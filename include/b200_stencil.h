@@ -141,6 +141,26 @@ int b200_sweep(const b200_sweep_desc* desc, void* const* arrays, void* stream);
  * per-sweep b200_wait / b200_signal ordering). */
 int b200_sweep_loop(const b200_sweep_desc* desc, void** arrays, int niters, void* stream);
 
+/* Temporal blocking: TWO sweeps in one pass over memory, for the tests where it is implemented
+ * (b200_sweep2_supported: jacobi, gaussblur, gameoflife).  arrays = { w0 (state t), w1 (only its
+ * boundary shell is read: the values state t+1 has on the global boundary), out (receives state
+ * t+2 in the interior; must already hold w0's boundary shell) }.  Per point the arithmetic is
+ * that of two b200_sweep calls, so the result is bit-identical; state t+1 is never written.
+ * Replaces two iterations of the nt-loop (e.g. gameoflife/gameoflife.c:276-289).  Single GPU. */
+int b200_sweep2_supported(int test);
+/* 1 when b200_run / b200_sweep_loop2 would use the fused kernel for this test and row length (a measured
+ * policy: today jacobi with nx >= 1024; B200_FUSE=1 / 0 forces it on / off). */
+int b200_sweep2_profitable(int test, int nx);
+int b200_sweep2(const b200_sweep_desc* desc, void* const* arrays, void* stream);
+
+/* b200_sweep_loop with a scratch buffer (same size as the arrays, holding arrays[0]'s boundary
+ * shell): runs (niters-2)/2 fused pairs followed by the remaining single sweeps, so that the last
+ * two states (the ones the reference driver reports, laplacian/laplacian.c:307-313) are both in
+ * memory.  After a pair the buffer that held state t becomes the scratch: arrays[] AND *scratch
+ * are updated in place.  Falls back to b200_sweep_loop when b200_sweep2_profitable() says no,
+ * scratch is NULL or niters < 4. */
+int b200_sweep_loop2(const b200_sweep_desc* desc, void** arrays, void** scratch, int niters, void* stream);
+
 /* The nt-loop of one z-slab whose neighbours are other processes / GPUs: `niters` sweeps back to
  * back, each pushing its boundary planes into the neighbours' copy of the array it writes
  * (peer_lo[] / peer_hi[]: the neighbours' buffers in the SAME rotation order as arrays[], peer

@@ -27,7 +27,7 @@ MAX_ARRAYS, MAX_SCALARS = 8, 8
 
 # every symbol include/b200_stencil.h declares (checked by tests/test_abi.py)
 EXPORTS = ["b200_get_test_info", "b200_test_by_name", "b200_last_error", "b200_api_version",
-           "b200_interior_points", "b200_device_count", "b200_sweep", "b200_sweep_loop", "b200_slab_loop", "b200_kernel_info",
+           "b200_interior_points", "b200_device_count", "b200_sweep", "b200_sweep_loop", "b200_sweep2_supported", "b200_sweep2_profitable", "b200_sweep2", "b200_sweep_loop2", "b200_slab_loop", "b200_kernel_info",
            "b200_launch_count", "b200_init", "b200_plan", "b200_alloc", "b200_load", "b200_run",
            "b200_slot_interior_dead", "b200_load_shell", "b200_result_slot", "b200_save", "b200_free", "b200_destroy", "b200_host_alloc",
            "b200_host_free", "b200_device_alloc", "b200_device_free", "b200_ipc_export",
@@ -86,6 +86,10 @@ def load() -> C.CDLL:
     L.b200_device_count.argtypes = [C.POINTER(C.c_int)]
     L.b200_sweep.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.c_void_p]
     L.b200_sweep_loop.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    L.b200_sweep2_supported.argtypes = [C.c_int]
+    L.b200_sweep2_profitable.argtypes = [C.c_int, C.c_int]
+    L.b200_sweep2.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.c_void_p]
+    L.b200_sweep_loop2.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
     L.b200_slab_loop.argtypes = [C.POINTER(SweepDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.c_int, C.c_ulonglong, C.c_void_p]
     L.b200_kernel_info.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_char_p)]
@@ -181,6 +185,27 @@ def sweep_loop(test, dtype, nx, ny, ns, scalars, device_ptrs, niters, stream=0, 
     ptrs = (C.c_void_p * len(device_ptrs))(*device_ptrs)
     _check(load().b200_sweep_loop(C.byref(d), ptrs, niters, C.c_void_p(stream)))
     return [int(p) if p else 0 for p in ptrs]
+
+
+def sweep2_supported(test) -> bool:
+    return bool(load().b200_sweep2_supported(_tid(test)))
+
+
+def sweep2_profitable(test, nx) -> bool:
+    return bool(load().b200_sweep2_profitable(_tid(test), nx))
+
+
+def sweep_loop2(test, dtype, nx, ny, ns, scalars, device_ptrs, scratch_ptr, niters, stream=0):
+    """b200_sweep_loop2: fused two-sweep passes (temporal blocking) + the remaining single sweeps.  Returns
+    (rotated pointer list, scratch pointer) -- after a fused pass the old w0 buffer is the scratch."""
+    d = SweepDesc()
+    d.test, d.dtype, d.nx, d.ny, d.ns = _tid(test), _DT[dtype], nx, ny, ns
+    for i, v in enumerate(scalars):
+        d.scalars[i] = float(v)
+    ptrs = (C.c_void_p * len(device_ptrs))(*device_ptrs)
+    scr = C.c_void_p(scratch_ptr)
+    _check(load().b200_sweep_loop2(C.byref(d), ptrs, C.byref(scr), niters, C.c_void_p(stream)))
+    return [int(p) if p else 0 for p in ptrs], int(scr.value or 0)
 
 
 def slab_loop(test, dtype, nx, ny, ns, scalars, device_ptrs, peer_lo, peer_hi, niters, first_sweep,

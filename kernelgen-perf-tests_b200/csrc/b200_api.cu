@@ -271,6 +271,67 @@ int b200_sweep_loop(const b200_sweep_desc* desc, void** arrays, int niters, void
     return B200_OK;
 }
 
+// Fused two-sweep kernels exist for the three 2D stencils; whether a loop USES them is a measured policy:
+// the fused pass halves the DRAM traffic but its consumer warps do two sweeps' arithmetic per tile, and with 12
+// warps per SM that is latency-bound.  Measured on B200 (profiles/README.md): jacobi at nx >= 1024 gains 13-19 %,
+// jacobi at nx = 512 loses (5 overlapped x-tiles for 4), gaussblur (-17 %) and gameoflife (FP64 pipe, -25 %) lose.
+// B200_FUSE=1 forces the fused path wherever it exists, B200_FUSE=0 disables it (tests, A/B runs).
+static launch_fn fused_kernel(int test)
+{
+    switch (test) {
+    case B200_JACOBI: return launch_jacobi2;
+    case B200_GAUSSBLUR: return launch_gaussblur2;
+    case B200_GAMEOFLIFE: return launch_gameoflife2;
+    default: return nullptr;
+    }
+}
+static launch_fn fused_launch(int test, int nx)
+{
+    const char* e = getenv("B200_FUSE");           // read per call: tests toggle it
+    if (e) return atoi(e) ? fused_kernel(test) : nullptr;
+    return (test == B200_JACOBI && nx >= 1024) ? fused_kernel(test) : nullptr;
+}
+
+int b200_sweep2_supported(int test) { return fused_kernel(test) != nullptr; }
+int b200_sweep2_profitable(int test, int nx) { return fused_launch(test, nx) != nullptr; }
+
+int b200_sweep2(const b200_sweep_desc* desc, void* const* arrays, void* stream)
+{
+    if (int rc = check_sweep_args(desc, arrays)) return rc;
+    launch_fn fn = fused_kernel(desc->test);
+    if (!fn) { set_error("%s has no two-sweep kernel", g_tests[desc->test].name); return B200_ERR_ARG; }
+    if (desc->push_lo || desc->push_hi || desc->out_begin || desc->out_end) { set_error("b200_sweep2: whole grid on one GPU only"); return B200_ERR_ARG; }
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    DeviceInfo di;
+    if (int rc = probe_device(dev, &di)) return rc;
+    HostArgs a{desc, arrays, (cudaStream_t)stream, dev, di.num_sms};
+    return fn(desc->dtype, a);
+}
+
+int b200_sweep_loop2(const b200_sweep_desc* desc, void** arrays, void** scratch, int niters, void* stream)
+{
+    if (int rc = check_sweep_args(desc, arrays)) return rc;
+    launch_fn fn = fused_launch(desc->test, desc->nx);
+    const bool whole = !(desc->push_lo || desc->push_hi || desc->out_begin || desc->out_end);
+    int pairs = (fn && whole && scratch && *scratch && niters >= 4) ? (niters - 2) / 2 : 0;
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    DeviceInfo di;
+    if (int rc = probe_device(dev, &di)) return rc;
+    b200_sweep_desc d = *desc;
+    for (int p = 0; p < pairs; p++) {
+        void* three[3] = { arrays[0], arrays[1], *scratch };
+        d.reverse_order = (desc->reverse_order + p) & 1;
+        HostArgs a{&d, three, (cudaStream_t)stream, dev, di.num_sms};
+        if (int rc = fn(desc->dtype, a)) return rc;
+        void* w = arrays[0]; arrays[0] = *scratch; *scratch = w;      // state t+2 is the new w0
+    }
+    d = *desc;
+    d.reverse_order = (desc->reverse_order + pairs) & 1;
+    return b200_sweep_loop(&d, arrays, niters - 2 * pairs, stream);
+}
+
 int b200_slab_loop(const b200_sweep_desc* desc, void** arrays, void** peer_lo, void** peer_hi,
                    int niters, unsigned long long first_sweep, void* stream)
 {
@@ -418,6 +479,7 @@ struct b200_slab {
     int own_lo, own_hi;         // owned range in the split dimension (global coordinates)
     int mem_lo, mem_hi;         // stored range (owned + ghosts), global coordinates
     void* arr[B200_MAX_ARRAYS]; // slot order (ORIGINAL numbering; rotation is applied per sweep)
+    void* scratch;              // third buffer of the 2-buffer tests that have a fused two-sweep kernel (1 GPU)
     cudaStream_t stream;
     cudaEvent_t done[2];        // sweep-complete events, alternating
     cudaEvent_t t0, t1;         // timing
@@ -552,6 +614,16 @@ int b200_alloc(b200_ctx* c)
             // fails to write shows up in the comparison
             if (getenv("B200_POISON")) B200_CUDA(cudaMemset(s.arr[q], 0xFF, bytes ? bytes : 16));
         }
+        s.scratch = nullptr;
+        if (c->ngpus == 1 && fused_launch(c->test, c->nx)) {
+            size_t bytes = slab_elems(c, s, 0) * esz;
+            B200_CUDA(cudaMalloc(&s.scratch, bytes ? bytes : 16));
+            if (getenv("B200_POISON")) B200_CUDA(cudaMemset(s.scratch, 0xFF, bytes ? bytes : 16));
+            KernelInfo k2{};
+            if (c->test == B200_JACOBI) { if (int rc = info_jacobi2(c->dtype, &k2)) return rc; }
+            else if (c->test == B200_GAUSSBLUR) { if (int rc = info_gaussblur2(c->dtype, &k2)) return rc; }
+            else if (c->test == B200_GAMEOFLIFE) { if (int rc = info_gameoflife2(c->dtype, &k2)) return rc; }
+        }
         B200_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         B200_CUDA(cudaEventCreateWithFlags(&s.done[0], cudaEventDisableTiming));
         B200_CUDA(cudaEventCreateWithFlags(&s.done[1], cudaEventDisableTiming));
@@ -568,6 +640,8 @@ int b200_alloc(b200_ctx* c)
     c->allocated = true;
     return B200_OK;
 }
+
+static int upload_shell(b200_ctx* c, int slot, const void* host, bool to_scratch);
 
 int b200_load(b200_ctx* c, int slot, const void* host)
 {
@@ -587,6 +661,8 @@ int b200_load(b200_ctx* c, int slot, const void* host)
         B200_CUDA(cudaStreamSynchronize(c->slab[g].stream));
     }
     B200_CUDA(cudaSetDevice(c->slab[0].dev));
+    // the scratch buffer of the fused two-sweep kernels takes over w0's role: it needs w0's boundary shell
+    if (slot == 0 && c->slab[0].scratch) return upload_shell(c, 0, host, true);
     return B200_OK;
 }
 
@@ -602,13 +678,11 @@ int b200_slot_interior_dead(int test, int slot)
     }
 }
 
-int b200_load_shell(b200_ctx* c, int slot, const void* host)
+// Copies the points outside the interior box of the plan's test from `host` (a whole array) into the
+// slab buffers of `slot` (to_scratch: into the slabs' scratch buffers instead).
+static int upload_shell(b200_ctx* c, int slot, const void* host, bool to_scratch)
 {
-    if (!c || !c->allocated) { set_error("b200_load_shell: not allocated"); return B200_ERR_STATE; }
     const b200_test_info* ti = b200_get_test_info(c->test);
-    if (slot < 0 || slot >= ti->narrays || !host) { set_error("b200_load_shell: bad slot/pointer"); return B200_ERR_ARG; }
-    if (!b200_slot_interior_dead(c->test, slot)) return b200_load(c, slot, host);
-    if (c->test == B200_MATVEC || c->test == B200_VECADD || c->test == B200_SINCOS) return B200_OK;   // no shell at all
     const size_t esz = esz_of(c->dtype);
     const int nx = c->nx, ny = c->ny;
     const bool d3 = ti->ndims == 3;
@@ -618,7 +692,8 @@ int b200_load_shell(b200_ctx* c, int slot, const void* host)
     for (int g = 0; g < c->ngpus; g++) {
         b200_slab& s = c->slab[g];
         B200_CUDA(cudaSetDevice(s.dev));
-        char* dst = (char*)s.arr[slot];
+        char* dst = (char*)(to_scratch ? s.scratch : s.arr[slot]);
+        if (!dst) continue;
         const char* src = (const char*)host + c->unit * (size_t)s.mem_lo * esz;
         const int n_split = s.mem_hi - s.mem_lo;               // planes (3D) / rows (2D) stored on this slab
         const size_t rows = d3 ? (size_t)ny * n_split : (size_t)n_split;
@@ -661,6 +736,16 @@ int b200_load_shell(b200_ctx* c, int slot, const void* host)
     return B200_OK;
 }
 
+int b200_load_shell(b200_ctx* c, int slot, const void* host)
+{
+    if (!c || !c->allocated) { set_error("b200_load_shell: not allocated"); return B200_ERR_STATE; }
+    const b200_test_info* ti = b200_get_test_info(c->test);
+    if (slot < 0 || slot >= ti->narrays || !host) { set_error("b200_load_shell: bad slot/pointer"); return B200_ERR_ARG; }
+    if (!b200_slot_interior_dead(c->test, slot)) return b200_load(c, slot, host);
+    if (c->test == B200_MATVEC || c->test == B200_VECADD || c->test == B200_SINCOS) return B200_OK;   // no shell at all
+    return upload_shell(c, slot, host, false);
+}
+
 int b200_run(b200_ctx* c, int niters, b200_stats* stats)
 {
     if (!c || !c->allocated) { set_error("b200_run: not allocated"); return B200_ERR_STATE; }
@@ -675,7 +760,32 @@ int b200_run(b200_ctx* c, int niters, b200_stats* stats)
         B200_CUDA(cudaEventRecord(c->slab[g].t0, c->slab[g].stream));
     }
     const int out_pos = ti->rotation == 3 ? 2 : 1;     // position of the written array in rotated order
-    for (int it = 0; it < niters; it++) {
+    // temporal blocking (1 GPU, tests with a fused kernel): (niters-2)/2 two-sweep passes, then single sweeps so
+    // that the last two states -- the ones the reference reports -- are both in memory
+    int first_single = 0;
+    if (G == 1 && c->slab[0].scratch && niters >= 4) {
+        if (launch_fn fn = fused_launch(c->test, c->nx)) {
+            b200_slab& s = c->slab[0];
+            B200_CUDA(cudaSetDevice(s.dev));
+            const int pairs = (niters - 2) / 2;
+            for (int p = 0; p < pairs; p++) {
+                b200_sweep_desc d;
+                memset(&d, 0, sizeof(d));
+                d.test = c->test; d.dtype = c->dtype;
+                d.nx = c->nx; d.ny = c->ny; d.ns = c->ns;
+                memcpy(d.scalars, c->sc, sizeof(d.scalars));
+                d.reverse_order = p & 1;
+                void* three[3] = { s.arr[c->idxs[0]], s.arr[c->idxs[1]], s.scratch };
+                DeviceInfo di;
+                if (int rc = probe_device(s.dev, &di)) return rc;
+                HostArgs a{&d, three, s.stream, s.dev, di.num_sms};
+                if (int rc = fn(c->dtype, a)) return rc;
+                void* w = s.arr[c->idxs[0]]; s.arr[c->idxs[0]] = s.scratch; s.scratch = w;   // two swaps = the same roles
+            }
+            first_single = 2 * pairs;
+        }
+    }
+    for (int it = first_single; it < niters; it++) {
         for (int g = 0; g < G; g++) {
             b200_slab& s = c->slab[g];
             B200_CUDA(cudaSetDevice(s.dev));
@@ -818,6 +928,11 @@ int b200_free(b200_ctx* c)
                 B200_CUDA(cudaFree(s.arr[q]));
             }
             s.arr[q] = nullptr;
+        }
+        if (s.scratch) {
+            drop_tensor_maps_for(s.scratch, (const char*)s.scratch + slab_elems(c, s, 0) * esz + 1);
+            B200_CUDA(cudaFree(s.scratch));
+            s.scratch = nullptr;
         }
         B200_CUDA(cudaStreamDestroy(s.stream));
         B200_CUDA(cudaEventDestroy(s.done[0]));

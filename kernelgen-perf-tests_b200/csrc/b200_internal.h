@@ -48,6 +48,10 @@ B200_DECLARE_OP(jacobi)
 B200_DECLARE_OP(gaussblur)
 B200_DECLARE_OP(gameoflife)
 B200_DECLARE_OP(tricubic)
+// two sweeps in one pass (temporal blocking, b200_ops2d.cuh: Fused2D); arrays = { w0, w1, out }
+B200_DECLARE_OP(jacobi2)
+B200_DECLARE_OP(gaussblur2)
+B200_DECLARE_OP(gameoflife2)
 // bandwidth kernels (k_pointwise.cu)
 B200_DECLARE_OP(vecadd)
 B200_DECLARE_OP(matvec)

@@ -123,7 +123,7 @@ template <class Op> int launch_stream(const HostArgs& a)
 
     const size_t pitch = (size_t)P.nx * sizeof(T);
     bool aligned = (pitch % 16) == 0;
-    for (int q = 0; q < ti->narrays; q++) {
+    for (int q = 0; q < ti->narrays + Op::EXTRA_ARRAYS; q++) {
         if (!a.arrays[q]) { set_error("%s: array slot %d is NULL", ti->name, q); return B200_ERR_ARG; }
         P.arr[q] = a.arrays[q];
         if (((uintptr_t)a.arrays[q]) % 16) aligned = false;
@@ -153,8 +153,8 @@ template <class Op> int launch_stream(const HostArgs& a)
         if (int rc = get_done_counter(a.device, &P.done_counter)) return rc;
     }
 
-    P.ntx = (P.nx + Op::TX - 1) / Op::TX;
-    P.nty = (P.yhi - P.ylo + Op::TY - 1) / Op::TY;
+    P.ntx = (P.nx + tile_px<Op>() - 1) / tile_px<Op>();
+    P.nty = (P.yhi - P.ylo + tile_py<Op>() - 1) / tile_py<Op>();
 
     if (P.use_tma) {
         for (int s = 0; s < Op::NSTAGED; s++) {

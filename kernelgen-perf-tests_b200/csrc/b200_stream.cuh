@@ -99,7 +99,13 @@ struct alignas(64) OutMaps {
     CUtensorMap m[MAX_OUT];        // box TX x TY, x-tiles 1..
     CUtensorMap m0[MAX_OUT];       // box (TX - V) x TY, x-tile 0
 };
-struct NoTmaStore {                       // base of the Ops that keep the register store path
+struct NoTmaStore {                       // defaults of an Op; the register store path
+    // work-item grid: tile (i, j) has its thread-owned box at x = i*PX + OX, y = ylo + j*PY + OY.  Plain Ops
+    // own exactly what they write (PX = TX, PY = TY); the fused two-sweep Ops own a ring more than they
+    // write (overlapped tiling), so their pitch is smaller than the tile and the origin is shifted.
+    static constexpr bool PRED_STORE = true;   // branch-free predicated stores (measured per Op: profiles/README.md)
+    static constexpr int EXTRA_SMEM = 0;  // bytes of shared memory for the Op's own use (after the ring)
+    static constexpr int EXTRA_ARRAYS = 0; // arrays beyond the test's own (fused Ops: the output buffer, slot narrays)
     static constexpr int NOUT = 0;
     static constexpr int out_slot(int) { return -1; }
     static constexpr int out_dpl(int) { return 0; }
@@ -138,7 +144,8 @@ template <class Op> struct Geo {
     static constexpr int OUT_BYTES = NOUT * OUT_TILE_BYTES;              // one staging buffer: NOUT tiles
     static constexpr int HDR_BYTES = 256;                                // mbarriers
     static constexpr int RING_BYTES = Op::STAGES * STAGE_BYTES;
-    static constexpr int SMEM_BYTES = HDR_BYTES + 128 /*alignment slack*/ + RING_BYTES + OB * OUT_BYTES;
+    static constexpr int EXTRA_BYTES = round_up_c(Op::EXTRA_SMEM, 128);
+    static constexpr int SMEM_BYTES = HDR_BYTES + 128 /*alignment slack*/ + RING_BYTES + EXTRA_BYTES + OB * OUT_BYTES;
     static_assert(SMEM_BYTES <= 232448, "tile does not fit the 227 KB of shared memory");
     static_assert(NOUT <= MAX_OUT && OUT_TILE_BYTES % 128 == 0, "bad output tile");
     // ordinal of output slot SLOT among the Op's TMA-stored outputs
@@ -169,6 +176,7 @@ template <class Op, bool PUSH, bool TS = false> struct Ctx {
     static constexpr int V = G::V;
     const StreamParams& P;
     unsigned char* stages;      // base of the ring
+    unsigned char* extra;       // the Op's own shared memory (Op::EXTRA_SMEM bytes)
     unsigned char* ostage;      // TS: output staging buffer of this step
     int opitch, oshift;         // TS, per item: row pitch of the staging tile and the column it starts at (x-tile 0: TX-V, V)
     uint32_t st;                // ring stage of this step
@@ -181,6 +189,7 @@ template <class Op, bool PUSH, bool TS = false> struct Ctx {
     int xmode;                  // per item: 1 = whole vector inside [xlo,xhi) and 16-byte stores legal,
                                 //           2 = some elements inside, 0 = none
     int rows_valid;             // per item: tile rows [0, rows_valid) are inside [ylo, yhi)
+    int pvec, pmask;            // per item: store predicates -- whole-vector store / bit v: element v alone (edge vectors)
     unsigned idx0;              // per item: Y0 * nx + x  (element index of tile row 0 within a plane)
     long long poff;             // per step: s * nx * ny  (element offset of the output plane; warp-uniform)
 
@@ -194,6 +203,13 @@ template <class Op, bool PUSH, bool TS = false> struct Ctx {
         xmode = (all && P.vec_ok) ? 1 : (some ? 2 : 0);
         rows_valid = min(G::TY, P.yhi - Y0);
         idx0 = (unsigned)(Y0 * P.nx + x);
+        pvec = xmode == 1;
+        pmask = 0;
+        if (xmode == 2) {
+#pragma unroll
+            for (int v = 0; v < V; v++)
+                if (x + v >= P.xlo && x + v < P.xhi) pmask |= 1 << v;
+        }
         if constexpr (TS) {
             oshift = X0 == 0 ? V : 0;
             opitch = G::TX - oshift;
@@ -238,11 +254,48 @@ template <class Op, bool PUSH, bool TS = false> struct Ctx {
         }
     }
 
+    // Branch-free store: one predicated 16-byte store (interior vectors) plus V predicated element stores
+    // (edge vectors).  Predication instead of branches keeps a step one basic block, so the loads of the next
+    // rows are scheduled above the stores of this one.
+    B200_DEV static void st_vec_pred(T* dst, const T (&val)[V], int on)
+    {
+        if constexpr (sizeof(T) == 8) {
+            if constexpr (Op::STREAM_OUT)
+                asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.global.cs.v2.f64 [%1], {%2, %3}; }" ::"r"(on), "l"(dst), "d"(val[0]), "d"(val[1]) : "memory");
+            else
+                asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.global.v2.f64 [%1], {%2, %3}; }" ::"r"(on), "l"(dst), "d"(val[0]), "d"(val[1]) : "memory");
+        } else {
+            if constexpr (Op::STREAM_OUT)
+                asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.global.cs.v4.f32 [%1], {%2, %3, %4, %5}; }" ::"r"(on), "l"(dst), "f"(val[0]), "f"(val[1]), "f"(val[2]), "f"(val[3]) : "memory");
+            else
+                asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.global.v4.f32 [%1], {%2, %3, %4, %5}; }" ::"r"(on), "l"(dst), "f"(val[0]), "f"(val[1]), "f"(val[2]), "f"(val[3]) : "memory");
+        }
+    }
+    B200_DEV static void st_elem_pred(T* dst, T val, int on)
+    {
+        if constexpr (sizeof(T) == 8)
+            asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.global.f64 [%1], %2; }" ::"r"(on), "l"(dst), "d"(val) : "memory");
+        else
+            asm volatile("{ .reg .pred p; setp.ne.s32 p, %0, 0; @p st.global.f32 [%1], %2; }" ::"r"(on), "l"(dst), "f"(val) : "memory");
+    }
+    B200_DEV void put_pred(T* dst, const T (&val)[V], int row_ok) const
+    {
+        st_vec_pred(dst, val, pvec & row_ok);
+#pragma unroll
+        for (int v = 0; v < V; v++) st_elem_pred(dst + v, val[v], (pmask >> v) & row_ok);
+    }
+
     // Store V results of output array SLOT at tile row `row` of the step's output plane (plane s
     // for the 3D tests, the only plane for the 2D tests); interior-predicated.
     // dplane: store into plane s + dplane instead (no halo push for those).
     template <int SLOT> B200_DEV void store(int row, const T (&val)[V], int dplane = 0) const
     {
+        if constexpr (Op::PRED_STORE && !PUSH && !(TS && G::out_q(SLOT) >= 0)) {
+            // the common case: branch-free
+            const unsigned off = idx0 + (unsigned)(row * P.nx);
+            put_pred(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val, row < rows_valid ? 1 : 0);
+            return;
+        }
         if (row >= rows_valid || xmode == 0) return;
         const unsigned off = idx0 + (unsigned)(row * P.nx);
         if constexpr (TS && G::out_q(SLOT) >= 0) {
@@ -344,6 +397,14 @@ template <class Op, int A> struct ProducerIssue {
 
 struct ItemCoords { int X0, Y0, za, zb; };
 
+// tile pitch / origin: an Op may declare PX, PY, OX, OY (fused two-sweep Ops); default = the tile itself
+template <class Op, class = void> struct TileGrid { static constexpr int PX = Op::TX, PY = Op::TY, OX = 0, OY = 0; };
+template <class Op> struct TileGrid<Op, decltype((void)Op::PX)> { static constexpr int PX = Op::PX, PY = Op::PY, OX = Op::OX, OY = Op::OY; };
+template <class Op> constexpr int tile_px() { return TileGrid<Op>::PX; }
+template <class Op> constexpr int tile_py() { return TileGrid<Op>::PY; }
+template <class Op> constexpr int tile_ox() { return TileGrid<Op>::OX; }
+template <class Op> constexpr int tile_oy() { return TileGrid<Op>::OY; }
+
 template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int item)
 {
     const int tiles_xy = P.ntx * P.nty;
@@ -352,8 +413,8 @@ template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int i
     const int t = item - zc * tiles_xy;
     const int tyi = t / P.ntx, txi = t - tyi * P.ntx;
     ItemCoords c;
-    c.X0 = txi * Op::TX;                       // x tiles start at 0 so vectors stay 16-byte aligned
-    c.Y0 = P.ylo + tyi * Op::TY;
+    c.X0 = txi * tile_px<Op>() + tile_ox<Op>();        // multiples of V: vectors stay 16-byte aligned
+    c.Y0 = P.ylo + tyi * tile_py<Op>() + tile_oy<Op>();
     c.za = P.z0 + zc * P.zc_len;
     c.zb = min(P.z1, c.za + P.zc_len);
     return c;
@@ -379,7 +440,8 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
     uint64_t* ofull = full + 2 * MAX_STAGES;       // [OB] staging buffer written by all consumer warps
     uint64_t* oempty = ofull + G::OB;              // [OB] staging buffer read out by the TMA store
     unsigned char* stages = smem + G::HDR_BYTES;
-    unsigned char* ostages = stages + G::RING_BYTES;
+    unsigned char* extra = stages + G::RING_BYTES;
+    unsigned char* ostages = extra + G::EXTRA_BYTES;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -476,7 +538,7 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
         // ------------------------------ consumer warps ------------------------------
         Op op(P);
         typename Op::State state;
-        Ctx<Op, PUSH, TS> ctx{P, stages, ostages, G::TX, 0, 0u, 0, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0, 0u, 0ll};
+        Ctx<Op, PUSH, TS> ctx{P, stages, extra, ostages, G::TX, 0, 0u, 0, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0, 0u, 0ll};
         uint32_t st = 0, ph = 0, rel_st = (uint32_t)(S - Op::HOLD) % S;    // ring stage / parity of this step; stage to hand back
         uint32_t g = 0, og = 0;
         for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {

@@ -4,4 +4,5 @@
 
 namespace b200 {
 B200_DEFINE_OP(gameoflife, GameoflifeOp)
+B200_DEFINE_OP(gameoflife2, Gameoflife2Op)       // two sweeps per pass (temporal blocking)
 }  // namespace b200

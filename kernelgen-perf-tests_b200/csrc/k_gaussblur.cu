@@ -4,4 +4,5 @@
 
 namespace b200 {
 B200_DEFINE_OP(gaussblur, GaussblurOp)
+B200_DEFINE_OP(gaussblur2, Gaussblur2Op)       // two sweeps per pass (temporal blocking)
 }  // namespace b200

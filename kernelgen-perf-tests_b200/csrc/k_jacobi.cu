@@ -4,4 +4,5 @@
 
 namespace b200 {
 B200_DEFINE_OP(jacobi, JacobiOp)
+B200_DEFINE_OP(jacobi2, Jacobi2Op)       // two sweeps per pass (temporal blocking)
 }  // namespace b200

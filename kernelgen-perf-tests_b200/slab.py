@@ -138,6 +138,12 @@ class SlabEngine:
             t.uniform_(-1.0, 1.0, generator=g)           # in place: no temporaries next to 30+ GB slabs
             self.mem.append(m)
             self.t.append(t)
+        # temporal blocking (1 GPU, tests with a fused two-sweep kernel): a third buffer holding w0's shell
+        self.scratch = self.scratch_t = None
+        if world == 1 and pkg.capi.sweep2_profitable(test, nx):
+            self.scratch = _DevMem(pkg, self._slot_len(0), self.np_dtype)
+            self.scratch_t = self.scratch.tensor(torch)
+            self.scratch_t.copy_(self.t[0])
         self.idxs = [0, 1, 2]
         self.sweeps_done = 0
         self.peer = {}
@@ -229,8 +235,16 @@ class SlabEngine:
                 ptrs = [m.ptr for m in self.mem]
                 for q in range(rot):
                     ptrs[q] = self.mem[self.idxs[q]].ptr
-                capi.sweep_loop(self.test, self.real, nx, ny, ns, self.scalars, ptrs, niters, stream=stream,
-                                out_range=out_range)
+                if self.scratch is not None and out_range is None:
+                    _, scr = capi.sweep_loop2(self.test, self.real, nx, ny, ns, self.scalars, ptrs, self.scratch.ptr,
+                                              niters, stream=stream)
+                    if scr != self.scratch.ptr:      # an odd number of fused passes: old w0 buffer <-> scratch
+                        q = next(i for i, m in enumerate(self.mem) if m.ptr == scr)
+                        self.mem[q], self.scratch = self.scratch, self.mem[q]
+                        self.t[q], self.scratch_t = self.scratch_t, self.t[q]
+                else:
+                    capi.sweep_loop(self.test, self.real, nx, ny, ns, self.scalars, ptrs, niters, stream=stream,
+                                    out_range=out_range)
             for _ in range(niters):
                 if rot == 2:
                     self.idxs[0], self.idxs[1] = self.idxs[1], self.idxs[0]
@@ -428,6 +442,9 @@ class SlabEngine:
         self.t = []
         for m in self.mem:
             m.free()
+        if self.scratch is not None:
+            self.scratch_t = None
+            self.scratch.free()
         if hasattr(self, "flags"):
             self.flags.free()
 
@@ -461,7 +478,8 @@ def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3):
                     rows.append({"test": test, "real": real, "size": f"{dims[0]}x{dims[1]}x{dims[2]}", "cfg": label,
                                  "us_per_sweep": round(sec * 1e6, 2), "glups": round(lups / sec / 1e9, 2),
                                  "gbs": round(lups * bpl / sec / 1e9, 1), "frac": round(lups * bpl / sec / 1e9 / peak_gbs, 4),
-                                 "regs": pkg.kernel_info(test, real)["regs"]})
+                                 "regs": pkg.kernel_info(test, real)["regs"],
+                                 "passes_per_10_sweeps": 6 if eng.scratch is not None else 10})
                     eng.close()
                 except Exception as e:      # keep the headline alive; report the failure
                     rows.append({"test": test, "real": real, "cfg": label, "error": str(e)[:200]})

@@ -58,7 +58,7 @@ def check(test, real, nx, ny, ns, nt, scalars, inputs, got, want, strict_want=No
 
 @pytest.mark.parametrize("real", ["float", "double"])
 @pytest.mark.parametrize("test", FIXTURE_TESTS)
-def test_golden_fixtures(ctx, test, real):
+def test_golden_fixtures(ctx, pkg, test, real):
     """Against outputs of the reference itself (shipped flags and strict build)."""
     fx = np.load(GOLDEN_DIR / f"{test}_{real}.npz")
     nx, ny, ns, nt = [int(v) for v in fx["dims"]]
@@ -75,7 +75,8 @@ def test_golden_fixtures(ctx, test, real):
         # vs the shipped (fast-math) build only a pointwise-relative bound is meaningful
         rtol = 1e-8 if real == "double" else 1e-2
         assert np.allclose(got[0], shipped[0], rtol=rtol, atol=0) and np.allclose(got[1], shipped[1], rtol=rtol, atol=0)
-    assert stats["launches"] == nt
+    pairs = (nt - 2) // 2 if (nt >= 4 and pkg.capi.sweep2_profitable(test, nx)) else 0
+    assert stats["launches"] == nt - pairs          # a fused two-sweep pass is one launch
 
 
 SIZES_3D = [(128, 20, 12), (130, 37, 29), (63, 31, 29), (260, 19, 11), (16, 5, 5), (5, 5, 5)]
@@ -118,6 +119,41 @@ def test_readme_size_double(ctx, pkg, test):
     fm_gpu = o.final_mean(test, "double", nx, ny, ns, got, slot)
     fm_ref = o.final_mean(test, "double", nx, ny, ns, want, slot)
     assert "%f" % fm_gpu == "%f" % fm_ref
+
+
+FUSED_SIZES = [(128, 70, 1), (130, 517, 1), (63, 301, 1), (512, 300, 1), (1024, 1203, 1), (248, 92, 1), (5, 5, 1), (9, 4, 1)]
+
+
+@pytest.mark.parametrize("real", ["float", "double"])
+@pytest.mark.parametrize("test", ["jacobi", "gaussblur", "gameoflife"])
+def test_fused_two_sweep_passes(pkg, oracle, oracle_strict, test, real, monkeypatch):
+    """Temporal blocking (b200_ops2d.cuh Fused2D, used by b200_run for the first nt-2 sweeps): bit-identical to
+    single sweeps (B200_FUSE=0), within the bar of the oracle; every array compared, buffers NaN-poisoned.
+    Sizes cover tile seams of the overlapped tiling (pitch 124 / 120 x 46 / 44 / 94 / 92), the scalar-loader
+    path (odd nx) and grids smaller than one tile."""
+    monkeypatch.setenv("B200_POISON", "1")
+    c = pkg.Context(1)
+    o = oracle_strict if test == "gameoflife" else oracle
+    try:
+        for nx, ny, ns in FUSED_SIZES:
+            for nt in (4, 7, 10):
+                scalars, inputs, _ = oracle.init(test, real, nx, ny, ns)
+                monkeypatch.setenv("B200_FUSE", "1")
+                a = [x.copy() for x in inputs]
+                slot_a, st_a = c.run_on_host_arrays(test, real, nx, ny, ns, scalars, a, nt)
+                monkeypatch.setenv("B200_FUSE", "0")
+                b = [x.copy() for x in inputs]
+                slot_b, st_b = c.run_on_host_arrays(test, real, nx, ny, ns, scalars, b, nt)
+                if pkg.interior_points(test, nx, ny, ns):      # an empty interior launches nothing
+                    assert st_b["launches"] == nt and st_a["launches"] == nt - (nt - 2) // 2, (st_a, st_b)
+                assert slot_a == slot_b
+                for q in range(len(a)):
+                    assert np.array_equal(a[q], b[q]), f"{test}/{real} {nx}x{ny} nt={nt}: slot {q}: fused != single sweeps"
+                want = [x.copy() for x in inputs]
+                assert o.run(test, real, nx, ny, ns, nt, scalars, want) == slot_a
+                check(test, real, nx, ny, ns, nt, scalars, inputs, a, want)
+    finally:
+        c.destroy()
 
 
 MATMUL_SIZES = [(128, 128, 128), (256, 64, 384), (130, 37, 29), (131, 67, 259), (16, 5, 5), (5, 5, 5), (1, 1, 1), (300, 513, 140)]
