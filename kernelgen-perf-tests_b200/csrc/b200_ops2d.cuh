@@ -143,7 +143,11 @@ template <typename T> struct GameoflifeK {
                 const double x = __dadd_rn((double)add(wc.at(v, 0), L), -3.);
                 const double y = __dadd_rn((double)L, -3.);
                 const double den = __dadd_rn(1., __dmul_rn(__dmul_rn(x, y), Cbig));
+#ifdef B200_EXP_GOL_DDIV
                 o[v] = (T)__ddiv_rn(1., den);
+#else
+                o[v] = (T)__drcp_rn(den);          // correctly rounded 1/den == __ddiv_rn(1., den), fewer instructions
+#endif
             }
             emit(r, o);
             wm = wc;

@@ -137,7 +137,7 @@ template <typename T> struct Wave13ptOp : NoTmaStore {
 // ------------------------------------------------------------------------------------------
 template <typename T> struct DivergenceOp : NoTmaStore {
     using real = T;
-    static constexpr int NC = pick_nc<T>(384);
+    static constexpr int NC = 384;            // 3 staged arrays: a 16-warp tile would not fit the shared memory
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 5, HOLD = 0, WARM = 2, PERIOD = 2;
     static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 3;
