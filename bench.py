@@ -280,7 +280,12 @@ def main():
     suite = None
     want_suite = args.suite if args.suite != "auto" else ("full" if world == 1 else "none")
     if rank == 0 and world == 1 and want_suite != "none":
-        suite = slabmod.suite_table(pkg, peak, full=(want_suite == "full"), scalars=DEFAULT_SCALARS)
+        def cpu_row(t, r, a, b, c, nit):
+            dt, kind, cores, _ = cpu_time_steps(t, r, a, b, c, nit, 1, 1)
+            return {"cpu_glups": round(pkg.interior_points(t, a, b, c) * nit / dt / 1e9, 3), "cpu_kind": kind, "cpu_cores": cores}
+
+        suite = slabmod.suite_table(pkg, peak, full=(want_suite == "full"), scalars=DEFAULT_SCALARS,
+                                    cpu_fn=cpu_row if (want_suite == "full" and not args.no_cpu) else None)
         if want_suite == "full":
             suite += slabmod.matmul_table(pkg)
 

@@ -449,7 +449,7 @@ class SlabEngine:
             self.flags.free()
 
 
-def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3):
+def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3, cpu_fn=None):
     """GLUP/s and fraction of the HBM roofline for every test, float and double, on cuda:0."""
     import torch
     rows = []
@@ -481,6 +481,9 @@ def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3):
                                  "regs": pkg.kernel_info(test, real)["regs"],
                                  "passes_per_10_sweeps": 6 if eng.scratch is not None else 10})
                     eng.close()
+                    if cpu_fn is not None and label == "C1":
+                        # the gcc path on the box's host cores, same test / size / niters (one timed step)
+                        rows[-1].update(cpu_fn(test, real, dims[0], dims[1], dims[2], niters))
                 except Exception as e:      # keep the headline alive; report the failure
                     rows.append({"test": test, "real": real, "cfg": label, "error": str(e)[:200]})
                     torch.cuda.synchronize()
