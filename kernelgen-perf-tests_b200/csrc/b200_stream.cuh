@@ -562,7 +562,23 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
                     }
                 }
                 mbar_wait(&full[st], ph);
-                step_dispatch<Op, Ctx<Op, PUSH, TS>>(op, ctx, state, phase);
+                if constexpr (PUSH) {
+                    // Only the steps that really produce a neighbour's ghost plane (rows, for the 2D tests) run the
+                    // variant with the halo-push code; every other step runs the single-GPU step (branch-free
+                    // stores, no push tests).  The two Ctx types have the same layout.
+                    bool push_now;
+                    if (P.push_dim == 2)
+                        push_now = (P.push_lo && s >= P.push_lo_src && s < P.push_lo_src + P.push_lo_cnt) ||
+                                   (P.push_hi && s >= P.push_hi_src && s < P.push_hi_src + P.push_hi_cnt);
+                    else
+                        push_now = (P.push_lo && c.Y0 < P.push_lo_src + P.push_lo_cnt && c.Y0 + G::TY > P.push_lo_src) ||
+                                   (P.push_hi && c.Y0 < P.push_hi_src + P.push_hi_cnt && c.Y0 + G::TY > P.push_hi_src);
+                    using CtxPlain = Ctx<Op, false, TS>;
+                    if (push_now) step_dispatch<Op, Ctx<Op, true, TS>>(op, ctx, state, phase);
+                    else step_dispatch<Op, CtxPlain>(op, reinterpret_cast<const CtxPlain&>(ctx), state, phase);
+                } else {
+                    step_dispatch<Op, Ctx<Op, PUSH, TS>>(op, ctx, state, phase);
+                }
                 if constexpr (TS) {
                     if (emit) {
                         fence_proxy_async_smem();
