@@ -71,5 +71,46 @@ keep = [l for l in det.splitlines() if any(k in l for k in (
     "# NOTE: ncu flushes the caches before the launch, so dram write bytes miss the part of the output still dirty in L2\n"
     "# at kernel end; the steady-state traffic is in the _traffic.txt file.\n" + out + "\n".join(keep) + "\n")
 shutil.copy(G / f"bench_{tag}.json", P / f"{tag}_bench.json")
+
+# 4. every other kernel captured by make_profiles.sh: one line of key metrics each
+reps = sorted(p for p in G.glob(f"prof_*_{tag}.ncu-rep") if "wave13pt" not in p.name)
+if reps:
+    out = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py")] + [str(p) for p in reps],
+                         capture_output=True, text=True).stdout
+    (P / f"{tag}_ncu_all_kernels.txt").write_text(
+        "# ncu --set full --clock-control none, one launch per kernel (tools/ncu_one.sh; caches flushed before the launch, so\n"
+        "# dur_us is the isolated kernel and wr_MB misses what is still dirty in L2).  Columns: tools/ncu_summary.py KEYS.\n" + out)
+if (G / f"ref_cuda_{tag}.json").exists():
+    shutil.copy(G / f"ref_cuda_{tag}.json", P / f"{tag}_ref_cuda_target.json")
+
+# 5. the per-test table of the bench line, as markdown
+b = json.loads((G / f"bench_{tag}.json").read_text().strip().splitlines()[-1])
+tab, cpu = {}, {}
+for r in b.get("suite", []):
+    if r["test"] == "matmul":
+        continue
+    tab.setdefault(r["test"], {})[(r.get("cfg"), r["real"])] = r
+ref = {}
+if (P / f"{tag}_ref_cuda_target.json").exists():
+    for r in json.loads((P / f"{tag}_ref_cuda_target.json").read_text()):
+        ref[(r["test"], r["real"])] = r.get("glups")
+lines = ["| test | C1 d GLUP/s (frac) | C1 f GLUP/s (frac) | C2 d frac | C2 f frac | C3 d frac | gcc+OpenMP C1 d / f GLUP/s | reference cuda target C1 d / f GLUP/s |",
+         "|---|---|---|---|---|---|---|---|"]
+def cell(r, g=True):
+    if not r or "frac" not in r:
+        return "-"
+    return f"{r['glups']:.0f} ({r['frac']:.2f})" if g else f"{r['frac']:.2f}"
+for t, v in tab.items():
+    c1d, c1f = v.get(("C1", "double")), v.get(("C1", "float"))
+    lines.append(f"| {t} | {cell(c1d)} | {cell(c1f)} | {cell(v.get(('C2', 'double')), False)} | {cell(v.get(('C2', 'float')), False)} | "
+                 f"{cell(v.get(('C3', 'double')), False)} | {(c1d or {}).get('cpu_glups', '-')} / {(c1f or {}).get('cpu_glups', '-')} | "
+                 f"{ref.get((t, 'double'), '-')} / {ref.get((t, 'float'), '-')} |")
+for r in b.get("suite", []):
+    if r["test"] == "matmul" and "tflops" in r:
+        lines.append(f"| matmul {r['real']} 8192^3 | {r['tflops']} TFLOP/s | cuBLAS {r['cublas_tflops']} TFLOP/s | ratio {r['vs_cublas']} | | | | |")
+(P / f"{tag}_suite_table.md").write_text(
+    f"Per-test roofline table of `profiles/{tag}_bench.json` (`suite` key).  C1 = 512x256x256 (2D tests 512x65536), C2 = 1024x1024x512, "
+    f"C3 = 1024^3 double; frac = algorithmic bytes per sweep / time / {b['roofline']['peak']} GB/s (measured copy ceiling).\n\n" + "\n".join(lines) + "\n")
+print((P / f"{tag}_suite_table.md").read_text())
 print(open(P / f"{tag}_launch_summary.txt").read())
 print(open(P / f"{tag}_traffic.txt").read())

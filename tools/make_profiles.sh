@@ -15,3 +15,14 @@ timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:stream_kernel -s 30 -c 1 -f \
     -o gpurun_out/prof_wave13pt_${tag} python bench.py --steps 3 --warmup 3 --suite none --no-e2e --no-cpu > /dev/null 2>&1
 ls -la gpurun_out | grep ${tag}
+# one `--set full` capture per stencil kernel (double, README size) -> tools/collect_profiles.py writes <tag>_ncu_all_kernels.txt
+if [ "${ALL_KERNELS:-1}" = "1" ]; then
+  for t in laplacian divergence gradient uxx1 lapgsrb tricubic; do bash tools/ncu_one.sh $t double 512x256x256 $tag; done
+  for t in jacobi gaussblur gameoflife; do bash tools/ncu_one.sh $t double 512x65536x1 $tag; done
+  bash tools/ncu_one.sh gameoflife float 512x65536x1 $tag
+  bash tools/ncu_one.sh lapgsrb float 512x256x256 $tag
+  bash tools/ncu_one.sh tricubic float 512x256x256 $tag
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:matmul -c 4 -f -o gpurun_out/prof_matmul_$tag python tools/matmul_bench.py 4096 1 > gpurun_out/ncu_matmul_$tag.log 2>&1
+fi
+timeout 600 python tools/ref_cuda_table.py gpurun_out/ref_cuda_$tag.json > gpurun_out/ref_cuda_$tag.log 2>&1
+ls -la gpurun_out | grep ${tag}

@@ -26,13 +26,15 @@ def main():
     pkg.load()
     from kernelgen_perf_tests_b200 import slab as slabmod
     args = [a for a in sys.argv[1:]]
-    size, niters, out = "512x256x256", 10, None
+    size, niters, out, only = "512x256x256", 10, None, None
     while args:
         a = args.pop(0)
         if a == "--size":
             size = args.pop(0)
         elif a == "--niters":
             niters = int(args.pop(0))
+        elif a == "--tests":
+            only = args.pop(0).split(",")
         else:
             out = a
     nx, ny, ns = [int(v) for v in size.split("x")]
@@ -48,9 +50,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for test in pkg.TESTS:
-        if test == "matmul":
-            continue
+    # the first engine of a process group pays one-time costs (module load of the halo-push kernels, IPC
+    # mappings, NCCL warm-up) that 10 warm-up sweeps do not always cover: run a throw-away test first
+    tests = [t for t in pkg.TESTS if t != "matmul" and (only is None or t in only)]
+    for i, test in enumerate([tests[0]] + tests):
+        discard = i == 0
         info = pkg.test_info(test)
         for real in ("double", "float"):
             dims = (nx, ny, ns) if info["ndims"] == 3 else (nx, ny * ns, 1)
@@ -74,6 +78,9 @@ def main():
                 sec = ms * 1e-3 / (reps * niters)
                 lups = eng.global_interior_points()
                 bpl = (info["nread"] + info["nwritten"]) * (4 if real == "float" else 8)
+                if discard:
+                    eng.close()
+                    continue
                 rows.append({"test": test, "real": real, "n_gpus": world, "slab": "x".join(str(d) for d in dims),
                              "us_per_sweep": round(sec * 1e6, 2), "glups": round(lups / sec / 1e9, 1),
                              "frac_per_gpu": round(lups * bpl / sec / 1e9 / world / peak, 4),
@@ -82,7 +89,7 @@ def main():
             except Exception as e:      # noqa: BLE001
                 rows.append({"test": test, "real": real, "n_gpus": world, "error": str(e)[:200]})
                 torch.cuda.synchronize()
-            if rank == 0:
+            if rank == 0 and rows and not discard:
                 print(rows[-1], flush=True)
     if rank == 0 and out:
         Path(out).write_text(json.dumps(rows, indent=1))
