@@ -71,7 +71,7 @@ if ! grep -q 'TARGETS_B200' "$SUITE/makefile"; then
     cat >> "$SUITE/makefile" <<'MK'
 
 ## ---- b200 target (added by kernelgen-perf-tests_b200/suite_overlay/install_overlay.sh) ----
-B200_TESTS = $(TARGETS) jacobi sincos
+B200_TESTS = $(TARGETS) jacobi sincos matmul
 TARGETS_B200 = $(addsuffix .b200, $(B200_TESTS))
 TARGETS_B200_CLEAN = $(addsuffix .b200.clean, $(B200_TESTS))
 

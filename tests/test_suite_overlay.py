@@ -31,7 +31,7 @@ def test_overlay_install_build_and_benchmark(tmp_path, pkg):
     subprocess.run(["chmod", "-R", "u+w", str(suite)], check=True)
     inst = ROOT / "kernelgen-perf-tests_b200" / "suite_overlay" / "install_overlay.sh"
     subprocess.run(["sh", str(inst), str(suite), str(ROOT)], check=True, capture_output=True)
-    for t in ("laplacian", "wave13pt", "jacobi", "gameoflife", "tricubic2", "matvec"):
+    for t in ("laplacian", "wave13pt", "jacobi", "gameoflife", "tricubic2", "matvec", "matmul", "sincos"):
         assert (suite / t / "b200" / "makefile").exists()
         assert (suite / t / "b200" / "kernel").read_text() == t
     bench = (suite / "benchmark").read_text()
@@ -39,7 +39,7 @@ def test_overlay_install_build_and_benchmark(tmp_path, pkg):
     # idempotent
     subprocess.run(["sh", str(inst), str(suite), str(ROOT)], check=True, capture_output=True)
     assert (suite / "benchmark").read_text() == bench
-    subprocess.run(["make", "-s", "laplacian.b200", "laplacian.gcc", "gameoflife.b200", "gameoflife.gcc"],
+    subprocess.run(["make", "-s", "laplacian.b200", "laplacian.gcc", "gameoflife.b200", "gameoflife.gcc", "matmul.b200"],
                    cwd=suite, check=True, capture_output=True)
     assert (suite / "laplacian" / "b200" / "laplacian").exists()
     out = subprocess.run(["./benchmark", "16", "8", "8", "1", "1", "b200", "gcc"], cwd=suite,
