@@ -377,12 +377,16 @@ template <typename T> struct LapgsrbOp : NoTmaStore {
 // ------------------------------------------------------------------------------------------
 template <typename T> B200_DEV void cubic_weights(T t, T (&w)[4])
 {
+    // 8 multiplies + 3 adds for the four weights (two shared two-factor products) instead of 12 + 3:
+    // the weights are 39 -> 33 of the ~120 FP64 instructions per point of a pipe-bound kernel
     const T sixth = (T)(1.0 / 6.0), half = (T)0.5;
     const T tm1 = t - (T)1, tp1 = t + (T)1, tp2 = t + (T)2;
-    w[0] = sixth * t * tp1 * tp2;
-    w[1] = -half * tm1 * tp1 * tp2;
-    w[2] = half * tm1 * t * tp2;
-    w[3] = -sixth * tm1 * t * tp1;
+    const T s = (sixth * t) * tp1;          // t (t+1) / 6
+    const T h = (half * tm1) * tp2;         // (t-1) (t+2) / 2
+    w[0] = s * tp2;
+    w[1] = -(h * tp1);
+    w[2] = h * t;
+    w[3] = -(s * tm1);
 }
 
 template <typename T> struct TricubicOp : NoTmaStore {
@@ -441,6 +445,85 @@ template <typename T> struct TricubicOp : NoTmaStore {
             }
             ctx.template store<1>(row, o);
         }
+    }
+};
+
+// Row-sharing form of the same stencil: a thread owns R ADJACENT rows (R * V points), so the u0 window
+// rows it reads from shared memory -- R + 3 per plane instead of 4 R -- are shared between its points.
+// Why: the one-row form is bound by shared-memory bandwidth (ncu: 85 % of the pipe's wavefronts; 16 window
+// rows of 40 bytes per 2 points = 2.7 clk per point per SM), not by HBM.  With R = 2 the window traffic drops
+// by 37.5 %.  The weights of R * V points (12 each) need more than 128 registers, so the Op runs 8 consumer
+// warps (+ the producer: 3+2+2+2 over the sub-partitions, 168 registers) -- the same number of points in
+// flight per SM as 12 warps x 1 row.  Per point the arithmetic and its order are those of TricubicOp
+// (x, then y in increasing jj, then z): bit-identical results.
+template <typename T, int R> struct TricubicRowsOp : NoTmaStore {
+    using real = T;
+    static constexpr int NC = 256;
+    static constexpr int TX = 128, TY = R * (NC / (TX / (16 / (int)sizeof(T)))), STAGES = 6, HOLD = 3, WARM = 3, PERIOD = 1;
+    static constexpr bool STREAM_OUT = false;
+    static constexpr int NSTAGED = 4;
+    static constexpr StagedSpec spec(int a)
+    {
+        return a == 0 ? StagedSpec{0, 1, 1, 2, 2, 1} : StagedSpec{a + 1, 0, 0, 0, 0, 0};
+    }
+    using G = Geo<TricubicRowsOp>;
+    static constexpr int V = G::V;
+    static_assert(G::CPT == R, "R adjacent rows per thread");
+    struct State { };
+    B200_DEV TricubicRowsOp(const StreamParams&) {}
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State&)
+    {
+        if (ctx.rel < 0) return;
+        constexpr int BW = G::bw(0);
+        const int row0 = R * ctx.ty;
+        T wa[R][V][4], wb[R][V][4], wc[R][V][4], o[R][V];
+        B200_UNROLL
+        for (int q = 0; q < R; q++) {
+            const VReg<T> va = ldv(ctx.template tile<1>(row0 + q)), vb = ldv(ctx.template tile<2>(row0 + q)),
+                          vc = ldv(ctx.template tile<3>(row0 + q));
+            B200_UNROLL
+            for (int v = 0; v < V; v++) {
+                cubic_weights(va[v], wa[q][v]);
+                cubic_weights(vb[v], wb[q][v]);
+                cubic_weights(vc[v], wc[q][v]);
+                o[q][v] = (T)0;
+            }
+        }
+        B200_UNROLL
+        for (int kk = 0; kk < 4; kk++) {
+            const T* p = ctx.template tile<0>(row0, 3 - kk);        // u0 plane s+kk-1, first owned row
+            T pz[R][V];
+            B200_UNROLL
+            for (int q = 0; q < R; q++) {
+                B200_UNROLL
+                for (int v = 0; v < V; v++) pz[q][v] = (T)0;
+            }
+            B200_UNROLL
+            for (int r = 0; r < R + 3; r++) {                       // window row row0 - 1 + r
+                Window<1, 2, T> w;
+                w.load(p + (r - 1) * BW);
+                B200_UNROLL
+                for (int q = 0; q < R; q++) {
+                    const int jj = r - q;                           // this window row is row jj of point row q
+                    if (jj >= 0 && jj <= 3) {
+                        B200_UNROLL
+                        for (int v = 0; v < V; v++) {
+                            const T px = ((wa[q][v][0] * w.at(v, -1) + wa[q][v][1] * w.at(v, 0)) + wa[q][v][2] * w.at(v, 1)) +
+                                         wa[q][v][3] * w.at(v, 2);
+                            pz[q][v] += wb[q][v][jj] * px;
+                        }
+                    }
+                }
+            }
+            B200_UNROLL
+            for (int q = 0; q < R; q++) {
+                B200_UNROLL
+                for (int v = 0; v < V; v++) o[q][v] += wc[q][v][kk] * pz[q][v];
+            }
+        }
+        B200_UNROLL
+        for (int q = 0; q < R; q++) ctx.template store<1>(row0 + q, o[q]);
     }
 };
 

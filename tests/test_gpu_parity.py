@@ -242,3 +242,25 @@ def test_kernel_info(pkg):
         for real in ("float", "double"):
             ki = pkg.kernel_info(t, real)
             assert 16 <= ki["regs"] <= 255 and ki["name"] == t
+
+
+def test_tricubic_row_variants():
+    """Both forms of the tricubic kernel (b200_ops3d.cuh: TricubicOp = one row per thread, TricubicRowsOp<2> =
+    two adjacent rows per thread, 8 warps) against the oracle, whichever is the default.  The library reads
+    B200_TRICUBIC_ROWS once per process, so each form runs in its own interpreter
+    (tests/tricubic_variant_check.py: tricubic + tricubic2, both precisions, ragged / odd / multi-tile sizes)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    out = {}
+    for rows in ("1", "2"):
+        env = dict(os.environ, B200_TRICUBIC_ROWS=rows)
+        p = subprocess.run([sys.executable, str(Path(__file__).resolve().parent / "tricubic_variant_check.py")],
+                           capture_output=True, text=True, env=env, timeout=900)
+        assert p.returncode == 0, f"rows={rows}: {p.stdout[-2000:]} {p.stderr[-2000:]}"
+        out[rows] = json.loads(p.stdout.strip().splitlines()[-1])
+        for real in ("float", "double"):
+            assert out[rows]["worst"][real] <= TOL[real], out[rows]
+    # same per-point arithmetic in the same order: reported, not required (the compiler is free to contract differently)
+    print("tricubic forms bit-identical:", out["1"]["sha"] == out["2"]["sha"], out)
