@@ -456,10 +456,10 @@ template <typename T> struct TricubicOp : NoTmaStore {
 // warps (+ the producer: 3+2+2+2 over the sub-partitions, 168 registers) -- the same number of points in
 // flight per SM as 12 warps x 1 row.  Per point the arithmetic and its order are those of TricubicOp
 // (x, then y in increasing jj, then z): bit-identical results.
-template <typename T, int R> struct TricubicRowsOp : NoTmaStore {
+template <typename T, int R, int NCV = 256, int STG = 6> struct TricubicRowsOp : NoTmaStore {
     using real = T;
-    static constexpr int NC = 256;
-    static constexpr int TX = 128, TY = R * (NC / (TX / (16 / (int)sizeof(T)))), STAGES = 6, HOLD = 3, WARM = 3, PERIOD = 1;
+    static constexpr int NC = NCV;
+    static constexpr int TX = 128, TY = R * (NC / (TX / (16 / (int)sizeof(T)))), STAGES = STG, HOLD = 3, WARM = 3, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 4;
     static constexpr StagedSpec spec(int a)

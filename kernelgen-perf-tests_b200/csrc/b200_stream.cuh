@@ -124,7 +124,7 @@ template <class Op> struct Geo {
     static constexpr int NTHREADS = NC + 32 + (Op::NOUT > 0 ? 32 : 0);     // + the producer warp (+ the store warp)
     static constexpr int LY = NC / LX;           // thread rows
     static constexpr int CPT = TY / LY;          // rows ("columns" in z) per thread
-    static_assert((NC == 256 || NC == 384 || NC == 512) && TX % V == 0 && NC % LX == 0 && TY % LY == 0, "bad tile");
+    static_assert((NC == 256 || NC == 320 || NC == 384 || NC == 512) && TX % V == 0 && NC % LX == 0 && TY % LY == 0, "bad tile");
     static constexpr int hxp(int a) { return Op::spec(a).hx ? V : 0; }
     static constexpr int bw(int a) { return TX + 2 * hxp(a); }
     static constexpr int bh(int a) { return TY + Op::spec(a).ylo + Op::spec(a).yhi; }
@@ -424,9 +424,9 @@ template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int i
 // four SM sub-partitions (16384 registers each) and warps are dealt round-robin, so 13 warps
 // (4+3+3+3) can have the full 128 registers per thread, while 16+1 warps or 2 CTAs x (8+1) warps
 // put 5 warps on one sub-partition and are limited to 96 -- which spills in every double kernel
-// (measured: profiles/README.md).  8 + 1 warps (3+2+2+2) may use 168: for the Ops that trade warps for
+// (measured: profiles/README.md).  8 + 1 warps (3+2+2+2) or 10 + 1 (3+3+3+2) may use 168: for the Ops that trade warps for
 // per-thread reuse (tricubic with two adjacent rows per thread).
-template <class Op> struct RegCap { static constexpr int value = Op::NC == 512 ? 96 : Op::NC == 256 ? 168 : 128; };
+template <class Op> struct RegCap { static constexpr int value = Op::NC == 512 ? 96 : Op::NC <= 320 ? 168 : 128; };
 
 template <class Op, bool PUSH, bool TS>
 __global__ void __launch_bounds__(Geo<Op>::NTHREADS) __maxnreg__(RegCap<Op>::value)

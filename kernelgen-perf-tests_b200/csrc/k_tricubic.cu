@@ -8,31 +8,37 @@
 
 namespace b200 {
 #ifndef B200_TRICUBIC_ROWS_F64
-#define B200_TRICUBIC_ROWS_F64 1
+#define B200_TRICUBIC_ROWS_F64 2
 #endif
 #ifndef B200_TRICUBIC_ROWS_F32
-#define B200_TRICUBIC_ROWS_F32 1
+#define B200_TRICUBIC_ROWS_F32 2
 #endif
 static int tricubic_rows(int dtype)
 {
     static const int env = getenv("B200_TRICUBIC_ROWS") ? atoi(getenv("B200_TRICUBIC_ROWS")) : 0;
     static const int env64 = getenv("B200_TRICUBIC_ROWS_F64") ? atoi(getenv("B200_TRICUBIC_ROWS_F64")) : 0;
     static const int env32 = getenv("B200_TRICUBIC_ROWS_F32") ? atoi(getenv("B200_TRICUBIC_ROWS_F32")) : 0;
-    if (env == 1 || env == 2) return env;
+    if (env >= 1 && env <= 3) return env;
     const int e = dtype == B200_F32 ? env32 : env64;
-    if (e == 1 || e == 2) return e;
+    if (e >= 1 && e <= 3) return e;
     return dtype == B200_F32 ? B200_TRICUBIC_ROWS_F32 : B200_TRICUBIC_ROWS_F64;
 }
+template <typename T> using Rows2 = TricubicRowsOp<T, 2>;                 // 8 consumer warps, 6-stage ring
+template <typename T> using Rows2W10 = TricubicRowsOp<T, 2, 320, 5>;      // 10 consumer warps, 5-stage ring
 int launch_tricubic(int dtype, const HostArgs& a)
 {
-    if (tricubic_rows(dtype) == 2)
-        return dtype == B200_F32 ? launch_stream<TricubicRowsOp<float, 2>>(a) : launch_stream<TricubicRowsOp<double, 2>>(a);
-    return dtype == B200_F32 ? launch_stream<TricubicOp<float>>(a) : launch_stream<TricubicOp<double>>(a);
+    switch (tricubic_rows(dtype)) {
+    case 2: return dtype == B200_F32 ? launch_stream<Rows2<float>>(a) : launch_stream<Rows2<double>>(a);
+    case 3: return dtype == B200_F32 ? launch_stream<Rows2W10<float>>(a) : launch_stream<Rows2W10<double>>(a);
+    default: return dtype == B200_F32 ? launch_stream<TricubicOp<float>>(a) : launch_stream<TricubicOp<double>>(a);
+    }
 }
 int info_tricubic(int dtype, KernelInfo* ki)
 {
-    if (tricubic_rows(dtype) == 2)
-        return dtype == B200_F32 ? info_stream<TricubicRowsOp<float, 2>>(ki, "tricubic") : info_stream<TricubicRowsOp<double, 2>>(ki, "tricubic");
-    return dtype == B200_F32 ? info_stream<TricubicOp<float>>(ki, "tricubic") : info_stream<TricubicOp<double>>(ki, "tricubic");
+    switch (tricubic_rows(dtype)) {
+    case 2: return dtype == B200_F32 ? info_stream<Rows2<float>>(ki, "tricubic") : info_stream<Rows2<double>>(ki, "tricubic");
+    case 3: return dtype == B200_F32 ? info_stream<Rows2W10<float>>(ki, "tricubic") : info_stream<Rows2W10<double>>(ki, "tricubic");
+    default: return dtype == B200_F32 ? info_stream<TricubicOp<float>>(ki, "tricubic") : info_stream<TricubicOp<double>>(ki, "tricubic");
+    }
 }
 }  // namespace b200

@@ -19,7 +19,8 @@
  * All GPU work goes through the C ABI of libb200stencil.so (include/b200_stencil.h); there
  * is no CPU fallback: any library error is printed like CUDA_SAFE_CALL does and exits with -1.
  *
- * Extra environment: B200_NGPUS=<1..8> cuts the grid into z-slabs over that many GPUs.
+ * Extra environment: B200_NGPUS=<1..8> cuts the grid into z-slabs over that many GPUs;
+ * B200_INIT_THREADS=<N> fills the host arrays with N threads in the same rand() draw order (kg_rand.h).
  */
 #include <malloc.h>
 #include <stdio.h>
@@ -39,8 +40,9 @@
 #define MEMALIGN 4096
 #define TEST B200_TEST_ID
 
-/* the reference's input generator, a double expression (laplacian.c:112) */
-#define real_rand() (((real)(rand() / (double)RAND_MAX) - 0.5) * 2)
+/* the reference's input generator real_rand() (laplacian.c:112) and the array fill, serial or -- with
+ * B200_INIT_THREADS=N -- parallel in the same draw order */
+#include "kg_init.h"
 
 #define parse_arg(name, arg) \
 	int name = atoi(arg); \
@@ -154,34 +156,27 @@ int main(int argc, char* argv[])
 
 	/* ---- init, element-interleaved across arrays (laplacian.c:158-165); matvec fills A, x, y
 	 * in three loops (matvec.c:119-134) ---- */
+	const int init_threads = kg_init_threads();
 	real mean = 0.0f;
 	if (TEST == B200_MATVEC)
 	{
-		real amean = 0.0f, xmean = 0.0f, ymean = 0.0f;
-		for (size_t i = 0; i < len[0]; i++) { a[0][i] = real_rand(); amean += a[0][i]; }
-		for (int i = 0; i < nx; i++) { a[1][i] = real_rand(); xmean += a[1][i]; }
-		for (int i = 0; i < ny; i++) { a[2][i] = real_rand(); ymean += a[2][i]; }
+		const real amean = kg_fill(&a[0], 1, len[0], init_threads);
+		const real xmean = kg_fill(&a[1], 1, (size_t)nx, init_threads);
+		const real ymean = kg_fill(&a[2], 1, (size_t)ny, init_threads);
 		if (!no_timing) printf("initial mean = %f\n", amean / (nx * ny) + xmean / nx + ymean / ny);
 	}
 	else if (TEST == B200_MATMUL)
 	{
 		/* matmul/main.c:98-110: A, then B; printed unconditionally.  The reference never
 		 * initialises C (fresh memalign pages read as zero); it is zeroed explicitly here. */
-		real meanA = 0.0f, meanB = 0.0f;
-		for (size_t i = 0; i < len[0]; i++) { a[0][i] = real_rand(); meanA += a[0][i]; }
-		for (size_t i = 0; i < len[1]; i++) { a[1][i] = real_rand(); meanB += a[1][i]; }
+		const real meanA = kg_fill(&a[0], 1, len[0], init_threads);
+		const real meanB = kg_fill(&a[1], 1, len[1], init_threads);
 		memset(a[2], 0, len[2] * sizeof(real));
 		printf("initial mean = %f\n", (meanA / len[0] + meanB / len[1]));
 	}
 	else
 	{
-		for (size_t i = 0; i < szarray; i++)
-		{
-			a[0][i] = real_rand();
-			real s = a[0][i];
-			for (int q = 1; q < na; q++) { a[q][i] = real_rand(); s = s + a[q][i]; }
-			mean += s;
-		}
+		mean = kg_fill(a, na, szarray, init_threads);
 		if (IMEAN_ALWAYS || !no_timing) printf("initial mean = %f\n", mean / szarray / na);
 	}
 

@@ -50,10 +50,12 @@ all: $t
 \$(B200_PKG)/libb200stencil.so:
 	\$(SILENT)\$(MAKE) -C \$(B200_PKG)/csrc
 
-$t: \$(B200_PKG)/drivers/driver.c \$(B200_PKG)/drivers/timing.c \$(B200_PKG)/libb200stencil.so
+B200_SRCS = \$(B200_PKG)/drivers/driver.c \$(B200_PKG)/drivers/timing.c \$(B200_PKG)/drivers/kg_rand.c
+
+$t: \$(B200_SRCS) \$(B200_PKG)/drivers/kg_init.h \$(B200_PKG)/libb200stencil.so
 	\$(SILENT)\$(GCC) -Dreal=\$(real) -DB200_TEST_ID=B200_$T -I\$(B200_ROOT)/include -I\$(B200_PKG)/drivers \\
-		\$(B200_PKG)/drivers/driver.c \$(B200_PKG)/drivers/timing.c -o \$@ \\
-		-L\$(B200_PKG) -lb200stencil -Wl,-rpath,\$(B200_PKG) -lrt -lm
+		\$(B200_SRCS) -o \$@ \\
+		-L\$(B200_PKG) -lb200stencil -Wl,-rpath,\$(B200_PKG) -lrt -lm -lpthread
 
 clean:
 	\$(SILENT)rm -rf *.o $t

@@ -69,6 +69,19 @@ def test_driver_contract_small(oracle, test, real):
         assert "%f" % sc[0] in first
 
 
+@pytest.mark.parametrize("test,real", [("laplacian", "double"), ("laplacian", "float"), ("uxx1", "float"),
+                                       ("gaussblur", "float"), ("matvec", "double"), ("tricubic", "double")])
+def test_parallel_init_same_inputs(test, real):
+    """B200_INIT_THREADS=N fills the host arrays with N threads in the reference's rand() draw order
+    (drivers/kg_rand.h): the inputs are bit-identical, hence the very same final mean; the initial mean may move
+    in its last digits (a `real` sum re-associated into per-thread partial sums)."""
+    dims = (96, 2048) if test in TWO_D else (96, 40, 48)
+    serial = parse_like_benchmark(run_driver(test, real, list(dims) + [3]), test)
+    par = parse_like_benchmark(run_driver(test, real, list(dims) + [3], env={"B200_INIT_THREADS": "8"}), test)
+    assert "%f" % serial["f_mean"] == "%f" % par["f_mean"], (serial, par)
+    assert abs(serial["i_mean"] - par["i_mean"]) <= (2e-6 if real == "double" else 1e-4)
+
+
 def test_readme_checksums_laplacian_wave13pt():
     """README.md:119,127 -- `./laplacian 512 256 256 10` and wave13pt, double."""
     for test, (gi, gf) in {"laplacian": (0.000041, 0.000011), "wave13pt": (0.000024, 0.000173)}.items():
