@@ -456,7 +456,9 @@ template <typename T> struct TricubicOp : NoTmaStore {
 // warps (+ the producer: 3+2+2+2 over the sub-partitions, 168 registers) -- the same number of points in
 // flight per SM as 12 warps x 1 row.  Per point the arithmetic and its order are those of TricubicOp
 // (x, then y in increasing jj, then z): bit-identical results.
-template <typename T, int R, int NCV = 256, int STG = 6> struct TricubicRowsOp : NoTmaStore {
+// SPLIT = true: a, b, c (read only at the step they arrive with) live in the shallower transient ring
+// (b200_stream.cuh: Op::transient), which pays for two more stages of u0 in flight.
+template <typename T, int R, int NCV = 256, int STG = 6, bool SPLIT = false> struct TricubicRowsOp : NoTmaStore {
     using real = T;
     static constexpr int NC = NCV;
     static constexpr int TX = 128, TY = R * (NC / (TX / (16 / (int)sizeof(T)))), STAGES = STG, HOLD = 3, WARM = 3, PERIOD = 1;
@@ -466,6 +468,7 @@ template <typename T, int R, int NCV = 256, int STG = 6> struct TricubicRowsOp :
     {
         return a == 0 ? StagedSpec{0, 1, 1, 2, 2, 1} : StagedSpec{a + 1, 0, 0, 0, 0, 0};
     }
+    static constexpr bool transient(int a) { return SPLIT && a > 0; }
     using G = Geo<TricubicRowsOp>;
     static constexpr int V = G::V;
     static_assert(G::CPT == R, "R adjacent rows per thread");

@@ -106,6 +106,14 @@ struct NoTmaStore {                       // defaults of an Op; the register sto
     static constexpr bool PRED_STORE = true;   // branch-free predicated stores (measured per Op: profiles/README.md)
     static constexpr int EXTRA_SMEM = 0;  // bytes of shared memory for the Op's own use (after the ring)
     static constexpr int EXTRA_ARRAYS = 0; // arrays beyond the test's own (fused Ops: the output buffer, slot narrays)
+    // transient(a): staged array a is read only at the step it arrives with (point-wise inputs of an Op whose
+    // other input is HELD in the ring for HOLD more steps).  Such arrays live in a second, shallower ring of
+    // STAGES - HOLD slots (slot = step mod that) instead of occupying every stage: the shared memory saved buys
+    // a deeper ring, i.e. more planes in flight.  No extra barriers: a stage's "empty" barrier completes only
+    // after the consumers are HOLD steps past it, so the producer is never more than STAGES - HOLD steps ahead
+    // of the slowest consumer -- except across an item boundary, where the held stages are handed back early;
+    // there the first WARM >= HOLD steps of the next item carry no transient data (see Geo's static_assert).
+    static constexpr bool transient(int) { return false; }
     static constexpr int NOUT = 0;
     static constexpr int out_slot(int) { return -1; }
     static constexpr int out_dpl(int) { return 0; }
@@ -130,20 +138,39 @@ template <class Op> struct Geo {
     static constexpr int bh(int a) { return TY + Op::spec(a).ylo + Op::spec(a).yhi; }
     static constexpr int box_bytes(int a) { return bw(a) * bh(a) * (int)sizeof(T); }
     static constexpr int arr_bytes(int a) { return round_up_c(box_bytes(a), 128); }
-    static constexpr int arr_off(int a)
+    static constexpr bool tr(int a) { return Op::transient(a); }
+    static constexpr int arr_off(int a)              // offset inside a stage of the array's own ring
     {
         int o = 0;
-        for (int b = 0; b < a; b++) o += arr_bytes(b);
+        for (int b = 0; b < a; b++)
+            if (tr(b) == tr(a)) o += arr_bytes(b);
         return o;
     }
-    static constexpr int STAGE_BYTES = arr_off(Op::NSTAGED);
+    static constexpr int ring_stage_bytes(bool t)
+    {
+        int o = 0;
+        for (int b = 0; b < Op::NSTAGED; b++)
+            if (tr(b) == t) o += arr_bytes(b);
+        return o;
+    }
+    static constexpr int STAGE_BYTES = ring_stage_bytes(false);
+    static constexpr int TSTAGE_BYTES = ring_stage_bytes(true);          // 0 for most Ops
+    static constexpr int TSLOTS = Op::STAGES - Op::HOLD;                 // slots of the transient ring
+    static constexpr int TRING_OFF = Op::STAGES * STAGE_BYTES;
+    static_assert(TSTAGE_BYTES == 0 || (Op::HOLD > 0 && Op::WARM >= Op::HOLD), "transient arrays need WARM >= HOLD > 0");
+    // address of staged array A for ring stage `st` / transient slot `tst`
+    template <int A> B200_DEV static unsigned char* arr_ptr(unsigned char* stages, uint32_t st, uint32_t tst)
+    {
+        if constexpr (tr(A)) return stages + TRING_OFF + tst * TSTAGE_BYTES + arr_off(A);
+        else return stages + st * STAGE_BYTES + arr_off(A);
+    }
     static constexpr int NOUT = Op::NOUT;
     static constexpr bool TS = NOUT > 0;                                 // TMA-store output path
     static constexpr int OB = 2;                                         // output staging buffers
     static constexpr int OUT_TILE_BYTES = TX * TY * (int)sizeof(T);
     static constexpr int OUT_BYTES = NOUT * OUT_TILE_BYTES;              // one staging buffer: NOUT tiles
     static constexpr int HDR_BYTES = 256;                                // mbarriers
-    static constexpr int RING_BYTES = Op::STAGES * STAGE_BYTES;
+    static constexpr int RING_BYTES = Op::STAGES * STAGE_BYTES + (TSTAGE_BYTES ? TSLOTS * TSTAGE_BYTES : 0);
     static constexpr int EXTRA_BYTES = round_up_c(Op::EXTRA_SMEM, 128);
     static constexpr int SMEM_BYTES = HDR_BYTES + 128 /*alignment slack*/ + RING_BYTES + EXTRA_BYTES + OB * OUT_BYTES;
     static_assert(SMEM_BYTES <= 232448, "tile does not fit the 227 KB of shared memory");
@@ -170,7 +197,12 @@ template <class Op> struct Geo {
 // there: a store is a row test, one multiply-add for the 32-bit element offset and one 64-bit
 // address add off a warp-uniform plane pointer.  PUSH = this launch also stores halo planes into
 // a neighbour GPU's memory; single-GPU launches are compiled without that code.
-template <class Op, bool PUSH, bool TS = false> struct Ctx {
+// slot of the step in the transient ring: a member only for the Ops that have transient arrays (empty base otherwise,
+// so every other kernel keeps its Ctx layout)
+template <bool HAS> struct CtxTransient { static constexpr uint32_t tst = 0; };
+template <> struct CtxTransient<true> { uint32_t tst = 0; };
+
+template <class Op, bool PUSH, bool TS = false> struct Ctx : CtxTransient<Geo<Op>::TSTAGE_BYTES != 0> {
     using T = typename Op::real;
     using G = Geo<Op>;
     static constexpr int V = G::V;
@@ -222,7 +254,9 @@ template <class Op, bool PUSH, bool TS = false> struct Ctx {
     {
         uint32_t q = st;
         if (back) q = (st + (uint32_t)Op::STAGES - (uint32_t)back) % (uint32_t)Op::STAGES;
-        const T* base = reinterpret_cast<const T*>(stages + q * G::STAGE_BYTES + G::arr_off(A));
+        const T* base;
+        if constexpr (G::tr(A)) base = reinterpret_cast<const T*>(G::template arr_ptr<A>(stages, q, this->tst));   // back == 0
+        else base = reinterpret_cast<const T*>(stages + q * G::STAGE_BYTES + G::arr_off(A));
         return base + (row + Op::spec(A).ylo) * G::bw(A) + G::hxp(A) + V * tx;
     }
     B200_DEV int gx() const { return x; }
@@ -347,12 +381,12 @@ B200_DEV void step_dispatch(Op& op, const C& ctx, typename Op::State& state, int
 
 // Producer-side fallback: fill one staged box with bounds-checked scalar loads (zero fill outside).
 template <class Op, int A>
-B200_DEV void fallback_fill(const StreamParams& P, unsigned char* stage, int X0, int Y0, int plane, int lane)
+B200_DEV void fallback_fill(const StreamParams& P, unsigned char* arr, int X0, int Y0, int plane, int lane)
 {
     using G = Geo<Op>;
     using T = typename Op::real;
     constexpr int BW = G::bw(A), BH = G::bh(A);
-    T* dst = reinterpret_cast<T*>(stage + G::arr_off(A));
+    T* dst = reinterpret_cast<T*>(arr);
     const T* src = reinterpret_cast<const T*>(P.arr[Op::spec(A).slot]);
     const int gx0 = X0 - G::hxp(A), gy0 = Y0 - Op::spec(A).ylo;
     const bool zin = plane >= 0 && plane < P.ns;
@@ -389,8 +423,27 @@ template <class Op, int A> struct ProducerIssue {
     {
         if constexpr (A < Op::NSTAGED) {
             if (s + Op::spec(A).lead >= za - Op::spec(A).zlo)
-                fallback_fill<Op, A>(P, stage, X0, Y0, s + Op::spec(A).lead, lane);
+                fallback_fill<Op, A>(P, stage + Geo<Op>::arr_off(A), X0, Y0, s + Op::spec(A).lead, lane);
             ProducerIssue<Op, A + 1>::fallback(P, stage, X0, Y0, s, za, lane);
+        }
+    }
+    // Ops with transient arrays: two rings
+    B200_DEV static void tma2(const TensorMaps& M, unsigned char* stages, uint32_t st, uint32_t tst, uint64_t* bar, int X0, int Y0, int s, int za)
+    {
+        if constexpr (A < Op::NSTAGED) {
+            if (s + Op::spec(A).lead >= za - Op::spec(A).zlo)
+                tma_load_3d_hint(Geo<Op>::template arr_ptr<A>(stages, st, tst), &M.m[A], bar, X0 - Geo<Op>::hxp(A),
+                                 Y0 - Op::spec(A).ylo, s + Op::spec(A).lead,
+                                 Op::spec(A).dead ? L2_EVICT_FIRST : L2_EVICT_NORMAL);
+            ProducerIssue<Op, A + 1>::tma2(M, stages, st, tst, bar, X0, Y0, s, za);
+        }
+    }
+    B200_DEV static void fallback2(const StreamParams& P, unsigned char* stages, uint32_t st, uint32_t tst, int X0, int Y0, int s, int za, int lane)
+    {
+        if constexpr (A < Op::NSTAGED) {
+            if (s + Op::spec(A).lead >= za - Op::spec(A).zlo)
+                fallback_fill<Op, A>(P, Geo<Op>::template arr_ptr<A>(stages, st, tst), X0, Y0, s + Op::spec(A).lead, lane);
+            ProducerIssue<Op, A + 1>::fallback2(P, stages, st, tst, X0, Y0, s, za, lane);
         }
     }
 };
@@ -500,9 +553,11 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
                     uint32_t bytes = 0;
                     ProducerIssue<Op, 0>::bytes(s, c.za, bytes);
                     mbar_arrive_expect_tx(&full[st], bytes);
-                    ProducerIssue<Op, 0>::tma(M, sb, &full[st], c.X0, c.Y0, s, c.za);
+                    if constexpr (G::TSTAGE_BYTES != 0) ProducerIssue<Op, 0>::tma2(M, stages, st, g % (uint32_t)G::TSLOTS, &full[st], c.X0, c.Y0, s, c.za);
+                    else ProducerIssue<Op, 0>::tma(M, sb, &full[st], c.X0, c.Y0, s, c.za);
                 } else {
-                    ProducerIssue<Op, 0>::fallback(P, sb, c.X0, c.Y0, s, c.za, lane);
+                    if constexpr (G::TSTAGE_BYTES != 0) ProducerIssue<Op, 0>::fallback2(P, stages, st, g % (uint32_t)G::TSLOTS, c.X0, c.Y0, s, c.za, lane);
+                    else ProducerIssue<Op, 0>::fallback(P, sb, c.X0, c.Y0, s, c.za, lane);
                     __threadfence_block();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full[st]);
@@ -539,7 +594,7 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
         // ------------------------------ consumer warps ------------------------------
         Op op(P);
         typename Op::State state;
-        Ctx<Op, PUSH, TS> ctx{P, stages, extra, ostages, G::TX, 0, 0u, 0, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0, 0u, 0ll};
+        Ctx<Op, PUSH, TS> ctx{{}, P, stages, extra, ostages, G::TX, 0, 0u, 0, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0, 0u, 0ll};
         uint32_t st = 0, ph = 0, rel_st = (uint32_t)(S - Op::HOLD) % S;    // ring stage / parity of this step; stage to hand back
         uint32_t g = 0, og = 0;
         for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
@@ -549,6 +604,7 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
             int local = 0, phase = 0;
             for (int s = c.za - Op::WARM; s < c.zb; ++s, ++g, ++local) {
                 ctx.st = st;
+                if constexpr (G::TSTAGE_BYTES != 0) ctx.tst = g % (uint32_t)G::TSLOTS;
                 ctx.s = s;
                 ctx.rel = s - c.za;
                 ctx.poff = (long long)s * P.nxny;
