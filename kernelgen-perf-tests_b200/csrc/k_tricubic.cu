@@ -8,7 +8,7 @@
 
 namespace b200 {
 #ifndef B200_TRICUBIC_ROWS_F64
-#define B200_TRICUBIC_ROWS_F64 2
+#define B200_TRICUBIC_ROWS_F64 4
 #endif
 #ifndef B200_TRICUBIC_ROWS_F32
 #define B200_TRICUBIC_ROWS_F32 2
