@@ -1,8 +1,13 @@
 // k_tricubic.cu -- instantiates the tricubic stencil (float + double) of the tile-streaming engine.
 //
-// Two forms of the same arithmetic (b200_ops3d.cuh): TricubicOp (12 warps, one row of V points per thread)
-// and TricubicRowsOp<T, 2> (8 warps, two adjacent rows per thread: 37.5 % less shared-memory traffic).
-// B200_TRICUBIC_ROWS[_F64|_F32]=1|2 overrides the per-precision default (A/B measurements: tools/tricubic_ab.py).
+// Four forms of the same arithmetic (b200_ops3d.cuh), bit-identical to each other:
+//   1  TricubicOp: 12 warps, one row of V points per thread (shared-memory bound);
+//   2  TricubicRowsOp<T, 2>: 8 warps at 168 registers, two adjacent rows per thread (37.5 % less shared-memory
+//      traffic) -- default for float;
+//   3  the same with 10 warps and a 5-stage ring (measured slower: kept as the measurement);
+//   4  form 2 with a, b, c in the engine's transient ring and 8 stages of u0 -- default for double.
+// B200_TRICUBIC_ROWS[_F64|_F32]=1..4 overrides the per-precision default (A/B: tools/r1r_run.sh, r1s_run.sh,
+// r1t_run.sh -> profiles/r1r_tricubic_ab.txt, r1t_tricubic_ab.txt).
 #include "b200_launch.cuh"
 #include "b200_ops3d.cuh"
 
