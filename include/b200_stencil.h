@@ -206,6 +206,19 @@ int b200_load_shell(b200_ctx* ctx, int slot, const void* host);
 int b200_run(b200_ctx* ctx, int niters, b200_stats* stats);
 int b200_result_slot(const b200_ctx* ctx);          /* slot (original numbering) the reference reports f_mean on */
 int b200_save(b200_ctx* ctx, int slot, void* host);
+/* Asynchronous mode (new: the reference's drivers synchronise after every phase, laplacian.c:255-262,303-305,
+ * 334-340).  With b200_set_async(ctx, 1) the phase calls b200_load / b200_load_shell / b200_run / b200_save only
+ * ENQUEUE their copies and sweeps on the context's own streams and return; b200_sync(ctx) waits for all of it.
+ * Host arrays must be pinned (b200_host_alloc) and stay untouched until b200_sync; b200_run fills no times
+ * (stats: launches, regs, name only).  Two contexts driven alternately overlap one job's device->host copy and
+ * sweeps with the next job's host->device copy (PCIe is full duplex): that is how bench.py's e2e leg and a
+ * driver that streams many grids through the GPU should call the library. */
+/* b200_rewind: start another job (load / run / save) on the buffers already planned and allocated: the rotation
+ * state returns to that of a fresh plan, so slot q means the reference's array q again (the reference starts a
+ * new process per job; its idxs[] starts at {0,1,2}, laplacian.c:269). */
+int b200_rewind(b200_ctx* ctx);
+int b200_set_async(b200_ctx* ctx, int on);
+int b200_sync(b200_ctx* ctx);
 int b200_free(b200_ctx* ctx);                       /* releases device buffers; ctx stays valid for re-plan */
 int b200_destroy(b200_ctx* ctx);
 

@@ -29,7 +29,7 @@ MAX_ARRAYS, MAX_SCALARS = 8, 8
 EXPORTS = ["b200_get_test_info", "b200_test_by_name", "b200_last_error", "b200_api_version",
            "b200_interior_points", "b200_device_count", "b200_sweep", "b200_sweep_loop", "b200_sweep2_supported", "b200_sweep2_profitable", "b200_sweep2", "b200_sweep_loop2", "b200_slab_loop", "b200_kernel_info",
            "b200_launch_count", "b200_init", "b200_plan", "b200_alloc", "b200_load", "b200_run",
-           "b200_slot_interior_dead", "b200_load_shell", "b200_result_slot", "b200_save", "b200_free", "b200_destroy", "b200_host_alloc",
+           "b200_slot_interior_dead", "b200_load_shell", "b200_result_slot", "b200_save", "b200_rewind", "b200_set_async", "b200_sync", "b200_free", "b200_destroy", "b200_host_alloc",
            "b200_host_free", "b200_device_alloc", "b200_device_free", "b200_ipc_export",
            "b200_ipc_import", "b200_ipc_close", "b200_signal", "b200_wait"]
 IPC_HANDLE_BYTES = 64
@@ -103,6 +103,9 @@ def load() -> C.CDLL:
     L.b200_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(Stats)]
     L.b200_result_slot.argtypes = [C.c_void_p]
     L.b200_save.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.b200_rewind.argtypes = [C.c_void_p]
+    L.b200_set_async.argtypes = [C.c_void_p, C.c_int]
+    L.b200_sync.argtypes = [C.c_void_p]
     L.b200_free.argtypes = [C.c_void_p]
     L.b200_destroy.argtypes = [C.c_void_p]
     L.b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
@@ -324,6 +327,17 @@ class Context:
     def save_array(self, slot: int, host: np.ndarray):
         assert host.flags.c_contiguous and host.dtype == NP_DTYPE[self.dtype]
         _check(load().b200_save(self.h, slot, host.ctypes.data_as(C.c_void_p)))
+
+    def rewind(self):
+        """Next load / run / save is a fresh job on the same buffers (rotation state as after plan())."""
+        _check(load().b200_rewind(self.h))
+
+    def set_async(self, on: bool):
+        """Phase calls only enqueue (host arrays must be pinned and stay untouched until sync())."""
+        _check(load().b200_set_async(self.h, 1 if on else 0))
+
+    def sync(self):
+        _check(load().b200_sync(self.h))
 
     def free(self):
         _check(load().b200_free(self.h))

@@ -496,7 +496,19 @@ struct b200_ctx {
     b200_slab slab[8];
     int idxs[3];                // rotation state, like the reference's idxs[] (laplacian.c:269,300)
     bool peer_enabled;
+    bool async_mode;            // b200_set_async: the phase calls enqueue only, b200_sync waits
 };
+
+// wait for the slabs' streams -- unless the context is in asynchronous mode (b200_set_async)
+static int sync_streams(b200_ctx* c, bool force = false)
+{
+    if (c->async_mode && !force) return B200_OK;
+    for (int g = 0; g < c->ngpus; g++) {
+        B200_CUDA(cudaSetDevice(c->slab[g].dev));
+        B200_CUDA(cudaStreamSynchronize(c->slab[g].stream));
+    }
+    return B200_OK;
+}
 
 static size_t esz_of(int dtype) { return dtype == B200_F32 ? 4 : 8; }
 
@@ -656,10 +668,7 @@ int b200_load(b200_ctx* c, int slot, const void* host)
         B200_CUDA(cudaMemcpyAsync(s.arr[slot], (const char*)host + off, slab_elems(c, s, slot) * esz,
                                   cudaMemcpyHostToDevice, s.stream));
     }
-    for (int g = 0; g < c->ngpus; g++) {
-        B200_CUDA(cudaSetDevice(c->slab[g].dev));
-        B200_CUDA(cudaStreamSynchronize(c->slab[g].stream));
-    }
+    if (int rc = sync_streams(c)) return rc;
     B200_CUDA(cudaSetDevice(c->slab[0].dev));
     // the scratch buffer of the fused two-sweep kernels takes over w0's role: it needs w0's boundary shell
     if (slot == 0 && c->slab[0].scratch) return upload_shell(c, 0, host, true);
@@ -728,10 +737,7 @@ static int upload_shell(b200_ctx* c, int slot, const void* host, bool to_scratch
                                                  (size_t)hiy * row_b, n_split, cudaMemcpyHostToDevice, s.stream));
         }
     }
-    for (int g = 0; g < c->ngpus; g++) {
-        B200_CUDA(cudaSetDevice(c->slab[g].dev));
-        B200_CUDA(cudaStreamSynchronize(c->slab[g].stream));
-    }
+    if (int rc = sync_streams(c)) return rc;
     B200_CUDA(cudaSetDevice(c->slab[0].dev));
     return B200_OK;
 }
@@ -853,7 +859,7 @@ int b200_run(b200_ctx* c, int niters, b200_stats* stats)
         B200_CUDA(cudaSetDevice(c->slab[g].dev));
         B200_CUDA(cudaEventRecord(c->slab[g].t1, c->slab[g].stream));
     }
-    for (int g = 0; g < G; g++) {
+    for (int g = 0; g < G && !c->async_mode; g++) {      // asynchronous mode: no wait, no times (b200_sync + own events)
         B200_CUDA(cudaSetDevice(c->slab[g].dev));
         B200_CUDA(cudaStreamSynchronize(c->slab[g].stream));
         float ms = 0.f;
@@ -905,10 +911,31 @@ int b200_save(b200_ctx* c, int slot, void* host)
         B200_CUDA(cudaMemcpyAsync((char*)host + dst_off, (const char*)s.arr[slot] + src_off,
                                   unit * (size_t)(s.own_hi - s.own_lo) * esz, cudaMemcpyDeviceToHost, s.stream));
     }
-    for (int g = 0; g < c->ngpus; g++) {
-        B200_CUDA(cudaSetDevice(c->slab[g].dev));
-        B200_CUDA(cudaStreamSynchronize(c->slab[g].stream));
-    }
+    if (int rc = sync_streams(c)) return rc;
+    B200_CUDA(cudaSetDevice(c->slab[0].dev));
+    return B200_OK;
+}
+
+int b200_rewind(b200_ctx* c)
+{
+    if (!c || !c->planned) { set_error("b200_rewind: not planned"); return B200_ERR_STATE; }
+    c->idxs[0] = 0; c->idxs[1] = 1; c->idxs[2] = 2;      // enqueue-order state only: legal while work is in flight
+    return B200_OK;
+}
+
+int b200_set_async(b200_ctx* c, int on)
+{
+    if (!c) { set_error("NULL context"); return B200_ERR_ARG; }
+    if (!on && c->async_mode && c->allocated) { if (int rc = sync_streams(c, true)) return rc; }
+    c->async_mode = on != 0;
+    return B200_OK;
+}
+
+int b200_sync(b200_ctx* c)
+{
+    if (!c) { set_error("NULL context"); return B200_ERR_ARG; }
+    if (!c->allocated) return B200_OK;
+    if (int rc = sync_streams(c, true)) return rc;
     B200_CUDA(cudaSetDevice(c->slab[0].dev));
     return B200_OK;
 }
@@ -917,6 +944,7 @@ int b200_free(b200_ctx* c)
 {
     if (!c) { set_error("NULL context"); return B200_ERR_ARG; }
     if (!c->allocated) return B200_OK;
+    if (int rc = sync_streams(c, true)) return rc;       // asynchronous mode: nothing may still be in flight
     const b200_test_info* ti = b200_get_test_info(c->test);
     const size_t esz = esz_of(c->dtype);
     for (int g = 0; g < c->ngpus; g++) {

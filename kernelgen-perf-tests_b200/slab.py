@@ -362,46 +362,72 @@ class SlabEngine:
         nbytes_in = sum(self._slot_len(q) for q in range(self.info["narrays"])) * esz
         if self.world == 1:
             nx, ny, ns = self.local_dims()
-            host = [capi.PinnedBuffer(self._slot_len(q), self.np_dtype) for q in range(self.info["narrays"])]
+            # Two contexts in asynchronous mode (b200_set_async), driven alternately by this one host thread: step i's
+            # device->host copy and sweeps overlap step i+1's host->device copy (PCIe is full duplex, the copies sit
+            # on each context's own stream).  Every step still uploads its own inputs from its own pinned buffers and
+            # downloads its own result inside the timed region.  B200_E2E_PIPELINE=0: one context, phase by phase.
+            import os
+            depth = 2 if os.environ.get("B200_E2E_PIPELINE", "1") != "0" else 1
             rng = np.random.default_rng(7)
-            for h in host:
-                h.array[:] = rng.uniform(-1, 1, h.array.size).astype(self.np_dtype)
-            ctx = capi.Context(1)
-            ctx.plan(self.test, self.real, nx, ny, ns if self.info["ndims"] == 3 else 1, self.scalars)
-            ctx.alloc()
+            lanes = []
+            for _ in range(depth):
+                host = [capi.PinnedBuffer(self._slot_len(q), self.np_dtype) for q in range(self.info["narrays"])]
+                for h in host:
+                    h.array[:] = rng.uniform(-1, 1, h.array.size).astype(self.np_dtype)
+                ctx = capi.Context(1)
+                ctx.plan(self.test, self.real, nx, ny, ns if self.info["ndims"] == 3 else 1, self.scalars)
+                ctx.alloc()
+                ctx.set_async(depth > 1)
+                lanes.append((ctx, host))
+            host = lanes[0][1]
 
             # what the C drivers do: output buffers (interior overwritten by the first sweep before anything
             # reads it) only send their boundary shell
-            dead = [ctx.interior_dead(q) for q in range(len(host))]
+            dead = [lanes[0][0].interior_dead(q) for q in range(len(host))]
             interior = self.pkg.interior_points(self.test, nx, ny, ns) if self.test not in ("matvec", "matmul") else 0
             nbytes_in = sum((h.array.size - interior if d and self.info["lo"][0] else (0 if d else h.array.size))
                             for h, d in zip(host, dead)) * esz
 
-            def step():
-                for q, h in enumerate(host):
+            def step(i):
+                ctx, hb = lanes[i % depth]
+                if depth > 1:
+                    ctx.sync()                    # this lane's previous step has left its host buffers
+                ctx.rewind()                      # a fresh job: slot q is the reference's array q again
+                for q, h in enumerate(hb):
                     if dead[q]:
                         ctx.load_array_shell(q, h.array)
                     else:
                         ctx.load_array(q, h.array)
                 ctx.run(niters)
                 slot = ctx.result_slot()
-                ctx.save_array(slot, host[slot].array)
+                ctx.save_array(slot, hb[slot].array)
                 return slot
 
-            step()
-            torch.cuda.synchronize()
+            def drain():
+                for ctx, _ in lanes:
+                    ctx.sync()
+                torch.cuda.synchronize()
+
+            for i in range(depth):
+                step(i)
+            drain()
             t0 = time.perf_counter()
-            for _ in range(steps):
-                slot = step()
-            torch.cuda.synchronize()
+            for i in range(steps):
+                slot = step(i)
+            drain()
             dt = (time.perf_counter() - t0) / steps
             nbytes_out = host[slot].array.nbytes
-            ctx.free()
-            ctx.destroy()
-            for h in host:
-                h.free()
+            for ctx, hb in lanes:
+                ctx.set_async(False)
+                ctx.free()
+                ctx.destroy()
+                for h in hb:
+                    h.free()
+            api = "b200_load/b200_load_shell/b200_run/b200_save (C ABI, pinned host buffers)"
+            if depth > 1:
+                api += "; two contexts in b200_set_async mode, alternating (copy/compute overlap across steps)"
             return {"seconds_per_step": dt, "h2d_bytes_per_step": int(nbytes_in), "d2h_bytes_per_step": int(nbytes_out),
-                    "api": "b200_load/b200_load_shell/b200_run/b200_save (C ABI, pinned host buffers)", "steps": steps}
+                    "api": api, "steps": steps, "pipeline_depth": depth}
         host = [torch.empty(self._slot_len(q), dtype=self.t[q].dtype).pin_memory() for q in range(self.info["narrays"])]
         for h in host:
             h.uniform_(-1, 1)

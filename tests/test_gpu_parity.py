@@ -244,6 +244,70 @@ def test_kernel_info(pkg):
             assert 16 <= ki["regs"] <= 255 and ki["name"] == t
 
 
+@pytest.mark.parametrize("test,real,dims", [("wave13pt", "double", (130, 37, 29)), ("laplacian", "float", (128, 48, 40)),
+                                            ("jacobi", "double", (256, 301, 1)), ("gradient", "float", (64, 31, 29))])
+def test_async_contexts_match_sync(pkg, oracle, test, real, dims):
+    """b200_set_async / b200_sync: two contexts whose phase calls only enqueue, driven alternately over several jobs
+    with different inputs (what bench.py's e2e leg does), give bit for bit what the synchronous phases give."""
+    nx, ny, ns = dims
+    nt, jobs = 5, 4
+    info = pkg.test_info(test)
+    dt = np.float64 if real == "double" else np.float32
+    scalars = [0.4, -0.05, 0.03, 0.02, 0.01, 0.005][:info["nscalars"]]
+    rng = np.random.default_rng(11)
+    inputs = [[rng.uniform(-1, 1, oracle.array_len(test, q, nx, ny, ns)).astype(dt) for q in range(info["narrays"])]
+              for _ in range(jobs)]
+    want = []
+    sync_ctx = pkg.Context(1)
+    try:
+        for j in range(jobs):
+            w = [a.copy() for a in inputs[j]]
+            slot, _ = sync_ctx.run_on_host_arrays(test, real, nx, ny, ns, scalars, w, nt)
+            want.append((slot, w))
+    finally:
+        sync_ctx.destroy()
+    lanes = []
+    for _ in range(2):
+        c = pkg.Context(1)
+        c.plan(test, real, nx, ny, ns, scalars)
+        c.alloc()
+        c.set_async(True)
+        host = [pkg.capi.PinnedBuffer(a.size, dt) for a in inputs[0]]
+        lanes.append((c, host, []))
+    try:
+        def collect(lane):
+            c, host, pending = lane
+            c.sync()
+            for j, slot in pending:
+                assert slot == want[j][0]
+                assert np.array_equal(host[slot].array, want[j][1][slot]), f"{test}/{real}: job {j} differs in async mode"
+            pending.clear()
+        for j in range(jobs):
+            lane = lanes[j % 2]
+            collect(lane)                                  # the lane's previous job has left its host buffers
+            c, host, pending = lane
+            c.rewind()
+            for q, h in enumerate(host):
+                h.array[:] = inputs[j][q]
+                if c.interior_dead(q):
+                    c.load_array_shell(q, h.array)
+                else:
+                    c.load_array(q, h.array)
+            c.run(nt)
+            slot = c.result_slot()
+            c.save_array(slot, host[slot].array)
+            pending.append((j, slot))
+        for lane in lanes:
+            collect(lane)
+    finally:
+        for c, host, _ in lanes:
+            c.set_async(False)
+            c.free()
+            c.destroy()
+            for h in host:
+                h.free()
+
+
 def test_tricubic_row_variants():
     """Every form of the tricubic kernel (b200_ops3d.cuh: 1 = TricubicOp, one row per thread; 2 = TricubicRowsOp<2>,
     two adjacent rows per thread, 8 warps; 3 = the same with 10 warps and a 5-stage ring; 4 = 8 warps with a, b, c in
