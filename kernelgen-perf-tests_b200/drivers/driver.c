@@ -20,7 +20,9 @@
  * is no CPU fallback: any library error is printed like CUDA_SAFE_CALL does and exits with -1.
  *
  * Extra environment: B200_NGPUS=<1..8> cuts the grid into z-slabs over that many GPUs;
- * B200_INIT_THREADS=<N> fills the host arrays with N threads in the same rand() draw order (kg_rand.h).
+ * B200_INIT_THREADS=<N> fills the host arrays with N threads in the same rand() draw order (kg_rand.h);
+ * B200_PINNED_HOST=1 page-locks the host arrays.  PROFILING_LINENO is accepted and unused, as in the
+ * reference's cuda target (cuda_profiling.cu:21-26 stores it and never reads it).
  */
 #include <malloc.h>
 #include <stdio.h>
@@ -140,11 +142,24 @@ int main(int argc, char* argv[])
 	if (TEST == B200_MATMUL) { len[0] = (size_t)nx * ny; len[1] = (size_t)ny * ns; len[2] = (size_t)nx * ns; }  /* matmul/main.c:80-85 */
 	size_t szarrayb = szarray * sizeof(real);
 
+	/* B200_PINNED_HOST=1: page-locked host arrays (b200_host_alloc) instead of the reference's memalign
+	 * (laplacian.c:149-150), so that "data load time" / "data save time" run at PCIe rate instead of through
+	 * the CUDA driver's staging of pageable memory.  Off by default: page-locking itself takes time (untimed,
+	 * like every host allocation of the reference) and moves the CUDA context creation out of "init time". */
+	const char* pinned_env = getenv("B200_PINNED_HOST");
+	const int pinned = pinned_env && atoi(pinned_env) != 0;
 	real* a[B200_MAX_ARRAYS] = { 0 };
 	int ok = 1;
 	for (int q = 0; q < na; q++)
 	{
-		a[q] = (real*)memalign(MEMALIGN, len[q] * sizeof(real) + 16);
+		if (pinned)
+		{
+			void* ptr = NULL;
+			if (b200_host_alloc(&ptr, len[q] * sizeof(real) + 16) != B200_OK) ptr = NULL;
+			a[q] = (real*)ptr;
+		}
+		else
+			a[q] = (real*)memalign(MEMALIGN, len[q] * sizeof(real) + 16);
 		if (!a[q]) ok = 0;
 	}
 	if (!ok)
@@ -298,7 +313,11 @@ int main(int argc, char* argv[])
 	(void)szarrayb;
 
 	b200_destroy(ctx);
-	for (int q = 0; q < na; q++) free(a[q]);
+	for (int q = 0; q < na; q++)
+	{
+		if (pinned) b200_host_free(a[q]);
+		else free(a[q]);
+	}
 	fflush(stdout);
 	return 0;
 }

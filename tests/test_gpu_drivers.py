@@ -82,6 +82,14 @@ def test_parallel_init_same_inputs(test, real):
     assert abs(serial["i_mean"] - par["i_mean"]) <= (2e-6 if real == "double" else 1e-4)
 
 
+def test_pinned_host_arrays_same_result():
+    """B200_PINNED_HOST=1 (page-locked host arrays instead of memalign): same means, load/save lines still there."""
+    a = parse_like_benchmark(run_driver("wave13pt", "double", [96, 40, 48, 3]), "wave13pt")
+    b = parse_like_benchmark(run_driver("wave13pt", "double", [96, 40, 48, 3], env={"B200_PINNED_HOST": "1"}), "wave13pt")
+    assert "%f" % a["i_mean"] == "%f" % b["i_mean"] and "%f" % a["f_mean"] == "%f" % b["f_mean"]
+    assert b["t_load"] is not None and b["t_save"] is not None
+
+
 def test_readme_checksums_laplacian_wave13pt():
     """README.md:119,127 -- `./laplacian 512 256 256 10` and wave13pt, double."""
     for test, (gi, gf) in {"laplacian": (0.000041, 0.000011), "wave13pt": (0.000024, 0.000173)}.items():
