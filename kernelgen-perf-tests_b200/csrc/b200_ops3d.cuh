@@ -21,10 +21,13 @@ namespace b200 {
 // formed and out_{p-1} = acc_{p-1} + beta*C_p is emitted: two live values per point, no queue.
 // (beta is distributed over the z+1 term: a re-association.)
 // ------------------------------------------------------------------------------------------
+#ifndef B200_LAP_TYF
+#define B200_LAP_TYF 48          // float tile height (experiment builds: -DB200_LAP_TYF=24, tools/plan_model.py)
+#endif
 template <typename T> struct LaplacianOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 48 : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 1;
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? B200_LAP_TYF : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
