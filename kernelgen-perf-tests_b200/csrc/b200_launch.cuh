@@ -203,6 +203,61 @@ template <class Op> int info_stream(KernelInfo* ki, const char* name)
     return B200_OK;
 }
 
+// ---- small-grid tile policy (float forms of the 3D Ops) --------------------------------------------------
+// The decomposition's own ceiling, by the planner's rule (tools/plan_model.py is the same arithmetic in Python):
+//   fill  = items / (rounds x CTAs), zwork = len / (len + WARM), yfill = interior rows / (y-tiles x TY).
+// With few tiles (512 x 256 x 256: 4 x 6 tiles of 128 x 48) z must be cut into many short chunks, each paying its
+// warm-up planes; half-height tiles double the tile count.  Measured for float laplacian (experiment build,
+// profiles/r1y_laplacian_float_tile_height.txt): 0.68 -> 0.77 of the roofline at 512 x 256 x 256, 0.76 -> 0.75 at
+// 1024 x 1024 x 512 -- so the small form is taken only when the model promises more than SMALL_TILE_GAIN.
+// B200_TILE_POLICY = 0 (default this round: the small forms have not had their GPU parity run yet) always takes the
+// default form, 1 lets the model choose, 2 always takes the small form (parity tests of that form).
+template <class Op> double decomposition_score(const b200_test_info* ti, int nx, int ny, int ns, int grid_cap)
+{
+    const int ylen = ny - ti->lo[1] - ti->hi[1], nz = ns - ti->lo[2] - ti->hi[2];
+    if (ylen <= 0 || nz <= 0 || nx <= 0 || grid_cap <= 0) return 0.0;
+    const int ntx = (nx + tile_px<Op>() - 1) / tile_px<Op>(), nty = (ylen + tile_py<Op>() - 1) / tile_py<Op>();
+    int nzc = 1, len = nz;
+    plan_zchunks(ntx * nty, nz, Op::WARM, grid_cap, &nzc, &len);
+    const long long items = (long long)ntx * nty * nzc, rounds = (items + grid_cap - 1) / grid_cap;
+    const double fill = (double)items / (double)(rounds * grid_cap);
+    const double zwork = (double)len / (double)(len + Op::WARM);
+    const double yfill = (double)ylen / (double)(nty * tile_py<Op>());
+    return fill * zwork * yfill;
+}
+constexpr double SMALL_TILE_GAIN = 1.05;
+inline int tile_policy()
+{
+    static const int p = getenv("B200_TILE_POLICY") ? atoi(getenv("B200_TILE_POLICY")) : 0;
+    return p;
+}
+template <class Big, class Small> int launch_by_tile_policy(const HostArgs& a)
+{
+    const int pol = tile_policy();
+    if (pol == 2) return launch_stream<Small>(a);
+    if (pol == 1) {
+        const b200_sweep_desc& d = *a.desc;
+        const b200_test_info* ti = b200_get_test_info(d.test);
+        const bool whole = d.out_begin == 0 && d.out_end == 0 && !d.push_lo && !d.push_hi;   // slabs keep the default form
+        if (whole && ti->ndims == 3 &&
+            decomposition_score<Small>(ti, d.nx, d.ny, d.ns, a.num_sms) >
+                SMALL_TILE_GAIN * decomposition_score<Big>(ti, d.nx, d.ny, d.ns, a.num_sms))
+            return launch_stream<Small>(a);
+    }
+    return launch_stream<Big>(a);
+}
+// a 3D Op whose float form has a half-height variant (template <typename T, int TYF>)
+#define B200_DEFINE_OP_TILED(name, OpT, TYF_SMALL)                                              \
+    int launch_##name(int dtype, const HostArgs& a)                                            \
+    {                                                                                          \
+        return dtype == B200_F32 ? launch_by_tile_policy<OpT<float>, OpT<float, TYF_SMALL>>(a) \
+                                 : launch_stream<OpT<double>>(a);                              \
+    }                                                                                          \
+    int info_##name(int dtype, KernelInfo* ki)                                                 \
+    {                                                                                          \
+        return dtype == B200_F32 ? info_stream<OpT<float>>(ki, #name) : info_stream<OpT<double>>(ki, #name); \
+    }
+
 #define B200_DEFINE_OP(name, OpT)                                                              \
     int launch_##name(int dtype, const HostArgs& a)                                            \
     {                                                                                          \

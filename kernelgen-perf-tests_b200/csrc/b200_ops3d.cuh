@@ -21,13 +21,12 @@ namespace b200 {
 // formed and out_{p-1} = acc_{p-1} + beta*C_p is emitted: two live values per point, no queue.
 // (beta is distributed over the z+1 term: a re-association.)
 // ------------------------------------------------------------------------------------------
-#ifndef B200_LAP_TYF
-#define B200_LAP_TYF 48          // float tile height (experiment builds: -DB200_LAP_TYF=24, tools/plan_model.py)
-#endif
-template <typename T> struct LaplacianOp : NoTmaStore {
+// TYF: tile height of the float form.  The second value each 3D Op is instantiated with (half the default) is the
+// small-grid form of b200_launch.cuh: launch_by_tile_policy (more tiles, hence fewer and longer z-chunks).
+template <typename T, int TYF = 48> struct LaplacianOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? B200_LAP_TYF : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 1;
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? TYF : 24, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 1;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
@@ -78,13 +77,13 @@ template <typename T> struct LaplacianOp : NoTmaStore {
 //     acc_p      = m0*C_p + inplane_p + m1*C_{p-1} + m2*C_{p-2}
 // rings of two: acc[PH&1] = acc_s, acc[(PH+1)&1] = acc_{s+1}; Cq[PH&1] = C_s, Cq[(PH+1)&1] = C_{s+1}.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct Wave13ptOp : NoTmaStore {
+template <typename T, int TYF = 24> struct Wave13ptOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
 #ifdef B200_EXP_WAVE_TY18
     static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 36 : 18, NC, 128), STAGES = 5, HOLD = 0, WARM = 4, PERIOD = 2;
 #else
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 4, PERIOD = 2;
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? TYF : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 4, PERIOD = 2;
 #endif
     static constexpr bool STREAM_OUT = false;
     static constexpr bool PRED_STORE = sizeof(T) == 4;      // measured: float +8 %, double -2 %
@@ -138,10 +137,10 @@ template <typename T> struct Wave13ptOp : NoTmaStore {
 // ring z[2]: z[PH] = uz plane s-1, z[PH^1] = plane s; plane s+1 arrives.
 // u is rewritten every sweep and never read: streamed past the L2.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct DivergenceOp : NoTmaStore {
+template <typename T, int TYF = 24> struct DivergenceOp : NoTmaStore {
     using real = T;
     static constexpr int NC = 384;            // 3 staged arrays: a 16-warp tile would not fit the shared memory
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 5, HOLD = 0, WARM = 2, PERIOD = 2;
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? TYF : 12, NC, 128), STAGES = 5, HOLD = 0, WARM = 2, PERIOD = 2;
     static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 3;
     static constexpr StagedSpec spec(int a)
@@ -188,10 +187,10 @@ template <typename T> struct DivergenceOp : NoTmaStore {
 // plane) and uz of plane s = gamma*(C_p - C_{s-1}).  ring Cq[2]: Cq[PH&1] = C_{s-1}, Cq[(PH+1)&1] = C_s.
 // The three outputs are rewritten every sweep and never read: streamed past the L2.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct GradientOp : NoTmaStore {
+template <typename T, int TYF = 24> struct GradientOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? TYF : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
     static constexpr bool STREAM_OUT = true;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
@@ -320,10 +319,10 @@ template <typename T> struct Uxx1Op : NoTmaStore {
 //     acc_p      = c0*C_p + c1*F_p + c2*D_p + c3*G_p + c1*C_{p-1} + c2*F_{p-1} + c3*C_{p-2}
 // Five live values per point: rings of two for acc and C, one F.  Re-associated.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct LapgsrbOp : NoTmaStore {
+template <typename T, int TYF = 24> struct LapgsrbOp : NoTmaStore {
     using real = T;
     static constexpr int NC = pick_nc<T>(384);
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? 24 : 12, NC, 128), STAGES = 8, HOLD = 0, WARM = 4, PERIOD = 2;
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? TYF : 12, NC, 128), STAGES = 8, HOLD = 0, WARM = 4, PERIOD = 2;
     static constexpr bool STREAM_OUT = false;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 2, 2, 2, 2}; }

@@ -3,5 +3,5 @@
 #include "b200_ops3d.cuh"
 
 namespace b200 {
-B200_DEFINE_OP(divergence, DivergenceOp)
+B200_DEFINE_OP_TILED(divergence, DivergenceOp, 12)
 }  // namespace b200

@@ -107,7 +107,7 @@ int launch_gradient(int dtype, const HostArgs& a)
     if (dbg == 4) return dtype == B200_F32 ? launch_stream<EngineFanoutOp<float, 0>>(a) : launch_stream<EngineFanoutOp<double, 0>>(a);
     if (dbg == 5) return dtype == B200_F32 ? launch_stream<EngineFanoutOp<float, 1>>(a) : launch_stream<EngineFanoutOp<double, 1>>(a);
     if (dbg) return dtype == B200_F32 ? launch_fanout<float>(a, dbg) : launch_fanout<double>(a, dbg);
-    return dtype == B200_F32 ? launch_stream<GradientOp<float>>(a) : launch_stream<GradientOp<double>>(a);
+    return dtype == B200_F32 ? launch_by_tile_policy<GradientOp<float>, GradientOp<float, 12>>(a) : launch_stream<GradientOp<double>>(a);
 }
 int info_gradient(int dtype, KernelInfo* ki)
 {

@@ -3,5 +3,5 @@
 #include "b200_ops3d.cuh"
 
 namespace b200 {
-B200_DEFINE_OP(lapgsrb, LapgsrbOp)
+B200_DEFINE_OP_TILED(lapgsrb, LapgsrbOp, 12)
 }  // namespace b200

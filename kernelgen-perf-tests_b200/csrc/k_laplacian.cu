@@ -6,7 +6,7 @@ namespace b200 {
 int launch_debug_copy(int dtype, const HostArgs& a, int mode);
 static int launch_laplacian_real(int dtype, const HostArgs& a)
 {
-    return dtype == B200_F32 ? launch_stream<LaplacianOp<float>>(a) : launch_stream<LaplacianOp<double>>(a);
+    return dtype == B200_F32 ? launch_by_tile_policy<LaplacianOp<float>, LaplacianOp<float, 24>>(a) : launch_stream<LaplacianOp<double>>(a);
 }
 int launch_laplacian(int dtype, const HostArgs& a)
 {

@@ -3,5 +3,5 @@
 #include "b200_ops3d.cuh"
 
 namespace b200 {
-B200_DEFINE_OP(wave13pt, Wave13ptOp)
+B200_DEFINE_OP_TILED(wave13pt, Wave13ptOp, 12)
 }  // namespace b200
