@@ -41,6 +41,36 @@ DEFAULT_SCALARS = {
 }
 
 
+# interior of every test, (ndims, lo, hi): lo[d] <= idx < n[d] - hi[d] -- the loop bounds of the reference kernels
+# (laplacian.c:81-99 ...).  Used by the reference arm, which must not map the product library.
+INTERIOR = {
+    "laplacian": (3, (1, 1, 1), (1, 1, 1)), "wave13pt": (3, (2, 2, 2), (2, 2, 2)), "divergence": (3, (1, 1, 1), (1, 1, 1)),
+    "gradient": (3, (1, 1, 1), (1, 1, 1)), "uxx1": (3, (2, 2, 2), (1, 1, 1)), "lapgsrb": (3, (2, 2, 2), (2, 2, 2)),
+    "jacobi": (2, (1, 1, 0), (1, 1, 0)), "gaussblur": (2, (2, 2, 0), (2, 2, 0)), "gameoflife": (2, (1, 1, 0), (1, 1, 0)),
+    "tricubic": (3, (1, 1, 1), (2, 2, 2)), "tricubic2": (3, (2, 2, 2), (2, 2, 2)), "vecadd": (3, (0, 0, 0), (0, 0, 0)),
+    "matvec": (2, (0, 0, 0), (0, 0, 0)), "sincos": (3, (0, 0, 0), (0, 0, 0)),
+}
+NARRAYS = {"laplacian": 2, "wave13pt": 3, "divergence": 4, "gradient": 4, "uxx1": 6, "lapgsrb": 2, "jacobi": 2,
+           "gaussblur": 2, "gameoflife": 2, "tricubic": 5, "tricubic2": 5, "vecadd": 3, "matvec": 3, "sincos": 3}
+
+
+def interior_points_py(test, nx, ny, ns):
+    """Lattice-point updates per sweep (same number as b200_interior_points; asserted equal in tests/test_abi.py)."""
+    nd, lo, hi = INTERIOR[test]
+    ext = [nx, ny * ns if nd == 2 else ny, 1 if nd == 2 else ns]
+    n = 1
+    for d in range(3):
+        n *= max(0, ext[d] - lo[d] - hi[d])
+    return n
+
+
+def make_config(test, real, nx, ny, ns, niters, world, halo):
+    """The `config` object of the JSON line -- ONE function for both arms, so the driver sees the same dict."""
+    return {"workload": f"{test} {nx}x{ny}x{ns} {real} niters={niters}" + (f" per GPU, z-slabs x{world}" if world > 1 else ""),
+            "l2": f"inputs larger than L2 ({NARRAYS[test]} x {nx * ny * ns * BYTES[real] / 1e6:.0f} MB per GPU vs 126 MB)",
+            "halo": halo if world > 1 else "none", "step": f"{niters} sweeps with buffer rotation"}
+
+
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -56,6 +86,7 @@ def parse_args():
     p.add_argument("--halo", default="push", choices=["push", "nccl"], help="N>1 ghost refresh")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-parity", action="store_true", help="N>1: skip the multi == single bit-identity check")
     return p.parse_args()
 
 
@@ -123,6 +154,11 @@ def cpu_time_steps(test, real, nx, ny, ns, niters, steps, warmup):
     import numpy as np
     import oracle_util as ou
     o = ou.Oracle("omp")
+    try:        # the OpenMP runtime may have been initialised (by torch) under torchrun's OMP_NUM_THREADS=1: set it explicitly
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(host_threads())
+    except OSError:
+        pass
     cores = o.max_threads()
     info = o.info(test)
     kind = "port"
@@ -156,24 +192,43 @@ def cpu_time_steps(test, real, nx, ny, ns, niters, steps, warmup):
     return dt, kind, cores, desc
 
 
+def host_threads():
+    """Host threads this process may use (affinity mask, not the machine total)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU legs want all host threads.  Must run
+    before the OpenMP runtime is loaded (libgomp reads the variable once), and the count is also set explicitly."""
+    n = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    return n
+
+
 def run_reference_arm(args, nx, ny, ns):
+    """--impl reference: the reference's own CPU kernel (oracle/_ref, built -fopenmp) on all host threads, with the
+    caller's --steps / --warmup, the same `config` dict as the b200 arm.  Under torchrun rank 0 alone works.  The
+    product library is NOT loaded here (interior points are computed in Python)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, str(ROOT))
-    from pkgload import load_pkg
-    pkg = load_pkg()
-    lups = pkg.interior_points(args.test, nx, ny, ns) * args.niters
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
+    use_all_host_threads()
+    lups = interior_points_py(args.test, nx, ny, ns) * args.niters
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     dt, kind, cores, desc = cpu_time_steps(args.test, args.real, nx, ny, ns, args.niters, steps, warm)
     val = lups / dt / 1e9
+    if world > 1:
+        desc += f" (bounded sample: ONE of the {world} slabs of the weak-scaled grid; GLUP/s of a CPU sweep does not depend on ns)"
     line = {
         "impl": "reference", "metric": "GLUP/s", "value": val, "unit": "GLUP/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": DTYPE_NAME[args.real], "data": "synthetic",
-        "config": {"workload": f"{args.test} {nx}x{ny}x{ns} {args.real} niters={args.niters}",
-                   "note": "reference CPU implementation of the path on the box's host cores (N GPUs do not apply)"},
+        "config": make_config(args.test, args.real, nx, ny, ns, args.niters, world, args.halo),
         "cpu_baseline": {"value": val, "unit": "GLUP/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -277,6 +332,16 @@ def main():
         cpu = {"value": pkg.interior_points(test, nx, ny, ns) * niters / dt / 1e9, "unit": "GLUP/s",
                "cores": cores, "kind": kind, "sample": desc}
 
+    # parity carried by the line itself (N > 1): the slab run == a single-GPU run of the same global grid, bit for bit --
+    # the headline test at the bench size, plus one 2D test (row push).  Outside the timed region.
+    parity = None
+    if world > 1 and info["exchange_slot"] >= 0 and not args.no_parity:
+        p3 = slabmod.multi_eq_single(pkg, dist, test, real, nx, ny, ns, scalars, niters, world, rank, halo=args.halo)
+        p2 = slabmod.multi_eq_single(pkg, dist, "gameoflife", "double", 1024, 4096, 1, [], niters, world, rank, halo=args.halo)
+        if rank == 0:
+            parity = {"multi_eq_single": bool(p3["multi_eq_single"] and p2["multi_eq_single"]),
+                      "bytes_compared": p3["bytes_compared"] + p2["bytes_compared"], "checks": [p3, p2]}
+
     suite = None
     want_suite = args.suite if args.suite != "auto" else ("full" if world == 1 else "none")
     if rank == 0 and world == 1 and want_suite != "none":
@@ -294,12 +359,12 @@ def main():
             "metric": "GLUP/s", "value": value, "unit": "GLUP/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": DTYPE_NAME[real], "data": "synthetic",
-            "config": {"workload": f"{test} {nx}x{ny}x{ns} {real} niters={niters}" + (f" per GPU, z-slabs x{world}" if world > 1 else ""),
-                       "l2": f"inputs larger than L2 ({info['narrays']} x {nx * ny * ns * BYTES[real] / 1e6:.0f} MB per GPU vs 126 MB)",
-                       "halo": args.halo if world > 1 else "none", "step": f"{niters} sweeps with buffer rotation"},
+            "config": make_config(test, real, nx, ny, ns, niters, world, args.halo),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if parity is not None:
+            line["parity"] = parity
         if suite is not None:
             line["suite"] = suite
         print(json.dumps(line), flush=True)

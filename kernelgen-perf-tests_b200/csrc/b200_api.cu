@@ -480,6 +480,7 @@ struct b200_slab {
     int mem_lo, mem_hi;         // stored range (owned + ghosts), global coordinates
     void* arr[B200_MAX_ARRAYS]; // slot order (ORIGINAL numbering; rotation is applied per sweep)
     void* scratch;              // third buffer of the 2-buffer tests that have a fused two-sweep kernel (1 GPU)
+    int scratch_shell_slot;     // the slot (arr[] numbering) whose boundary shell the scratch buffer carries, -1: none yet
     cudaStream_t stream;
     cudaEvent_t done[2];        // sweep-complete events, alternating
     cudaEvent_t t0, t1;         // timing
@@ -627,6 +628,7 @@ int b200_alloc(b200_ctx* c)
             if (getenv("B200_POISON")) B200_CUDA(cudaMemset(s.arr[q], 0xFF, bytes ? bytes : 16));
         }
         s.scratch = nullptr;
+        s.scratch_shell_slot = -1;
         if (c->ngpus == 1 && fused_launch(c->test, c->nx)) {
             size_t bytes = slab_elems(c, s, 0) * esz;
             B200_CUDA(cudaMalloc(&s.scratch, bytes ? bytes : 16));
@@ -671,7 +673,10 @@ int b200_load(b200_ctx* c, int slot, const void* host)
     if (int rc = sync_streams(c)) return rc;
     B200_CUDA(cudaSetDevice(c->slab[0].dev));
     // the scratch buffer of the fused two-sweep kernels takes over w0's role: it needs w0's boundary shell
-    if (slot == 0 && c->slab[0].scratch) return upload_shell(c, 0, host, true);
+    if (slot == 0 && c->slab[0].scratch) {
+        c->slab[0].scratch_shell_slot = 0;
+        return upload_shell(c, 0, host, true);
+    }
     return B200_OK;
 }
 
@@ -768,30 +773,37 @@ int b200_run(b200_ctx* c, int niters, b200_stats* stats)
     const int out_pos = ti->rotation == 3 ? 2 : 1;     // position of the written array in rotated order
     // temporal blocking (1 GPU, tests with a fused kernel): (niters-2)/2 two-sweep passes, then single sweeps so
     // that the last two states -- the ones the reference reports -- are both in memory
-    int first_single = 0;
-    if (G == 1 && c->slab[0].scratch && niters >= 4) {
-        if (launch_fn fn = fused_launch(c->test, c->nx)) {
+    // A fused pass writes state t+2 into the scratch buffer, which must carry the boundary shell of the array in the w0
+    // role (arr[idxs[0]]).  b200_load seeds it with slot 0's shell; after an ODD number of sweeps the roles are swapped
+    // (idxs = {1,0}), so a later b200_run first does ONE single sweep to realign them (`lead`), then the pairs.
+    int lead = 0, pairs = 0;
+    launch_fn fused = nullptr;
+    if (G == 1 && c->slab[0].scratch && c->slab[0].scratch_shell_slot >= 0 && (fused = fused_launch(c->test, c->nx))) {
+        lead = c->idxs[0] == c->slab[0].scratch_shell_slot ? 0 : 1;
+        pairs = niters - lead >= 4 ? (niters - lead - 2) / 2 : 0;
+    }
+    for (int it = 0; it < niters; it++) {
+        if (it == lead && pairs > 0) {
             b200_slab& s = c->slab[0];
             B200_CUDA(cudaSetDevice(s.dev));
-            const int pairs = (niters - 2) / 2;
             for (int p = 0; p < pairs; p++) {
                 b200_sweep_desc d;
                 memset(&d, 0, sizeof(d));
                 d.test = c->test; d.dtype = c->dtype;
                 d.nx = c->nx; d.ny = c->ny; d.ns = c->ns;
                 memcpy(d.scalars, c->sc, sizeof(d.scalars));
-                d.reverse_order = p & 1;
+                d.reverse_order = (lead + p) & 1;
                 void* three[3] = { s.arr[c->idxs[0]], s.arr[c->idxs[1]], s.scratch };
                 DeviceInfo di;
                 if (int rc = probe_device(s.dev, &di)) return rc;
                 HostArgs a{&d, three, s.stream, s.dev, di.num_sms};
-                if (int rc = fn(c->dtype, a)) return rc;
+                if (int rc = fused(c->dtype, a)) return rc;
                 void* w = s.arr[c->idxs[0]]; s.arr[c->idxs[0]] = s.scratch; s.scratch = w;   // two swaps = the same roles
             }
-            first_single = 2 * pairs;
+            it += 2 * pairs;
+            pairs = 0;
+            if (it >= niters) break;      // cannot happen (two single sweeps always follow), kept for safety
         }
-    }
-    for (int it = first_single; it < niters; it++) {
         for (int g = 0; g < G; g++) {
             b200_slab& s = c->slab[g];
             B200_CUDA(cudaSetDevice(s.dev));
@@ -926,6 +938,9 @@ int b200_rewind(b200_ctx* c)
 int b200_set_async(b200_ctx* c, int on)
 {
     if (!c) { set_error("NULL context"); return B200_ERR_ARG; }
+    // Multi-GPU contexts order neighbouring slabs' loads, halo pushes and saves through the host synchronisation that
+    // asynchronous mode removes (a neighbour's sweep-0 push could race a b200_load of the same buffer): single GPU only.
+    if (on && c->ngpus > 1) { set_error("b200_set_async: single-GPU contexts only (ngpus = %d)", c->ngpus); return B200_ERR_STATE; }
     if (!on && c->async_mode && c->allocated) { if (int rc = sync_streams(c, true)) return rc; }
     c->async_mode = on != 0;
     return B200_OK;

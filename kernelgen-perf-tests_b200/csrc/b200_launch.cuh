@@ -120,6 +120,8 @@ template <class Op> int launch_stream(const HostArgs& a)
         lo = d.out_begin; hi = d.out_end;
     }
     if (P.xhi <= P.xlo || P.yhi <= P.ylo || P.z1 <= P.z0) return B200_OK;   // empty interior: nothing to update
+    // in-plane element offsets are 32-bit in the kernels (Ctx::idx0, row * nx): refuse planes they cannot address
+    if (P.nxny >= 0x7fffffffLL) { set_error("%s: plane of %lld elements (nx*ny) exceeds the 2^31-1 the kernels index", ti->name, P.nxny); return B200_ERR_ARG; }
 
     const size_t pitch = (size_t)P.nx * sizeof(T);
     bool aligned = (pitch % 16) == 0;
@@ -210,8 +212,10 @@ template <class Op> int info_stream(KernelInfo* ki, const char* name)
 // warm-up planes; half-height tiles double the tile count.  Measured for float laplacian (experiment build,
 // profiles/r1y_laplacian_float_tile_height.txt): 0.68 -> 0.77 of the roofline at 512 x 256 x 256, 0.76 -> 0.75 at
 // 1024 x 1024 x 512 -- so the small form is taken only when the model promises more than SMALL_TILE_GAIN.
-// B200_TILE_POLICY = 0 (default this round: the small forms have not had their GPU parity run yet) always takes the
-// default form, 1 lets the model choose, 2 always takes the small form (parity tests of that form).
+// B200_TILE_POLICY = 1 (default; validated on the GPU in round 2: tests/test_gpu_parity.py::test_small_tile_forms_float,
+// byte-identical outputs, profiles/r2a_tile_policy.txt: laplacian float 0.689 -> 0.737, lapgsrb float 0.589 -> 0.611 at
+// 512 x 256 x 256, nothing lost at 1024 x 1024 x 512) lets the model choose, 0 always takes the default form, 2 always
+// takes the small form (parity tests of that form).
 template <class Op> double decomposition_score(const b200_test_info* ti, int nx, int ny, int ns, int grid_cap)
 {
     const int ylen = ny - ti->lo[1] - ti->hi[1], nz = ns - ti->lo[2] - ti->hi[2];
@@ -228,7 +232,7 @@ template <class Op> double decomposition_score(const b200_test_info* ti, int nx,
 constexpr double SMALL_TILE_GAIN = 1.05;
 inline int tile_policy()
 {
-    static const int p = getenv("B200_TILE_POLICY") ? atoi(getenv("B200_TILE_POLICY")) : 0;
+    static const int p = getenv("B200_TILE_POLICY") ? atoi(getenv("B200_TILE_POLICY")) : 1;
     return p;
 }
 template <class Big, class Small> int launch_by_tile_policy(const HostArgs& a)

@@ -29,6 +29,11 @@ namespace b200 {
 //   384 (12 warps): 13 warps = 4+3+3+3 over the four SM sub-partitions, 128 registers per thread;
 //   512 (16 warps): 17 warps put 5 on one sub-partition -> 96 registers per thread; for the Ops that
 //                   fit, a third more warps hide more latency and keep more stores in flight.
+// Experiment forms (-DB200_EXP_*) exist only in the diagnostics library (make diag: -DB200_DIAG): the product build refuses them.
+#if !defined(B200_DIAG) && (defined(B200_EXP_TS) || defined(B200_EXP_WAVE_TY18) || defined(B200_EXP_GOL_DDIV) || \
+                            defined(B200_EXP_NC32) || defined(B200_EXP_NC64))
+#error "B200_EXP_* forms are diagnostics: build them with `make diag EXTRA=-DB200_EXP_...`"
+#endif
 #ifndef B200_EXP_NC32
 #define B200_EXP_NC32 0
 #endif

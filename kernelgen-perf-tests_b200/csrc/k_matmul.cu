@@ -313,6 +313,7 @@ matmul_f32_kernel(int M, int N, int K, const float* __restrict__ A, int lda, con
     }
 }
 
+#ifdef B200_DIAG      // libb200stencil_diag.so only: the library GEMM as a baseline (B200_MATMUL=cublas)
 // ------------------------------------------------------------------------------------------
 // cuBLAS baseline (B200_MATMUL=cublas), resolved with dlopen at first use
 // ------------------------------------------------------------------------------------------
@@ -384,6 +385,8 @@ static int launch_cublas(int dtype, const HostArgs& a, int c0, int c1)
     return B200_OK;
 }
 
+#endif  // B200_DIAG
+
 // ------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------
@@ -429,9 +432,10 @@ int launch_matmul(int dtype, const HostArgs& a)
         c0 = d.out_begin; c1 = d.out_end;
     }
     if (c1 <= c0 || d.nx <= 0 || d.ny <= 0) return B200_OK;
-    const char* mode = getenv("B200_MATMUL");          // read per call: bench.py toggles it for the comparison
-    const bool use_cublas = mode && !strcmp(mode, "cublas");
-    if (use_cublas) return launch_cublas(dtype, a, c0, c1);
+#ifdef B200_DIAG
+    const char* mode = getenv("B200_MATMUL");
+    if (mode && !strcmp(mode, "cublas")) return launch_cublas(dtype, a, c0, c1);
+#endif
     return dtype == B200_F32 ? launch_tc<float>(a, c0, c1) : launch_tc<double>(a, c0, c1);
 }
 

@@ -144,6 +144,7 @@ class SlabEngine:
             self.scratch = _DevMem(pkg, self._slot_len(0), self.np_dtype)
             self.scratch_t = self.scratch.tensor(torch)
             self.scratch_t.copy_(self.t[0])
+        self.scratch_shell = 0          # index into self.mem whose boundary shell the scratch buffer carries
         self.idxs = [0, 1, 2]
         self.sweeps_done = 0
         self.peer = {}
@@ -236,8 +237,15 @@ class SlabEngine:
                 for q in range(rot):
                     ptrs[q] = self.mem[self.idxs[q]].ptr
                 if self.scratch is not None and out_range is None:
+                    n2 = niters
+                    if self.idxs[0] != self.scratch_shell and niters >= 1:
+                        # after an odd number of sweeps the w0 role is held by the OTHER buffer, whose shell the scratch
+                        # does not carry: one single sweep first realigns the roles (b200_run does the same)
+                        capi.sweep_loop(self.test, self.real, nx, ny, ns, self.scalars, ptrs, 1, stream=stream)
+                        ptrs[0], ptrs[1] = ptrs[1], ptrs[0]
+                        n2 = niters - 1
                     _, scr = capi.sweep_loop2(self.test, self.real, nx, ny, ns, self.scalars, ptrs, self.scratch.ptr,
-                                              niters, stream=stream)
+                                              n2, stream=stream)
                     if scr != self.scratch.ptr:      # an odd number of fused passes: old w0 buffer <-> scratch
                         q = next(i for i, m in enumerate(self.mem) if m.ptr == scr)
                         self.mem[q], self.scratch = self.scratch, self.mem[q]
@@ -318,6 +326,27 @@ class SlabEngine:
                 self.idxs = [self.idxs[1], self.idxs[2], self.idxs[0]]
             self.sweeps_done += 1
 
+    # -- deterministic contents (parity checks at any size) -------------------------------------
+    def fill_pattern(self, seed: int = 0):
+        """Every array becomes a fixed function of the GLOBAL element index (an integer hash mapped to [-1, 1)), so any
+        decomposition of the same global grid holds the same values at the same points, ghosts included -- no RNG state,
+        no host array, no exchange.  Stencil tests only (uniform slot layout)."""
+        torch, L = self.torch, self.layout
+        assert self.test not in ("matvec", "matmul")
+        chunk = 1 << 26
+        for q, t in enumerate(self.t):
+            base = L.mem_lo * self.unit
+            for a in range(0, t.numel(), chunk):
+                b = min(t.numel(), a + chunk)
+                e = torch.arange(base + a, base + b, device=t.device, dtype=torch.int64)
+                h = (e * 2654435761 + (q + 1) * 40503 + seed * 69069) & 0x7FFFFFFF
+                h = (h ^ (h >> 13)) * 1274126177 & 0x7FFFFFFF
+                t[a:b] = (h.to(torch.float64) * (2.0 / 2147483648.0) - 1.0).to(t.dtype)
+        if self.scratch_t is not None:
+            self.scratch_t.copy_(self.t[self.idxs[0]])
+            self.scratch_shell = self.idxs[0]
+        torch.cuda.synchronize()
+
     # -- scatter / gather of a global host array (tests) ---------------------------------------
     def set_global(self, q: int, full: np.ndarray):
         """Load this rank's slab (owned planes + ghosts) of slot q from the GLOBAL array."""
@@ -329,6 +358,9 @@ class SlabEngine:
         else:
             part = full[L.mem_lo * self.unit:L.mem_hi * self.unit]
         self.t[q].copy_(torch.from_numpy(np.ascontiguousarray(part)).to(self.t[q].device))
+        if self.scratch_t is not None and q == self.idxs[0]:
+            self.scratch_t.copy_(self.t[q])      # the fused path's third buffer carries the shell of the w0-role array
+            self.scratch_shell = q
 
     def get_owned(self, q: int) -> np.ndarray:
         """This rank's OWNED planes of slot q (no ghosts), as a host array."""
@@ -475,6 +507,65 @@ class SlabEngine:
             self.flags.free()
 
 
+def multi_eq_single(pkg, dist, test, real, nx, ny, ns, scalars, niters, world, rank, halo="push"):
+    """Parity carried by the number itself: the N-rank slab run and a 1-GPU run of the SAME global grid (per-GPU extents
+    nx x ny x ns, weak-scaled like the bench) on rank 0, from identical deterministic contents, `niters` sweeps each; the
+    owned planes of every rank are gathered to rank 0 and compared BIT FOR BIT with the single-GPU arrays.  Returns (on
+    rank 0) {"multi_eq_single": bool, "bytes_compared": n, ...}; None on the other ranks.  Outside any timed region."""
+    import torch
+    info = pkg.test_info(test)
+    eng = SlabEngine(pkg, test, real, nx, ny, ns, scalars, world=world, rank=rank, dist=dist, halo=halo)
+    eng.fill_pattern()
+    dist.barrier()
+    eng.run(niters)
+    torch.cuda.synchronize()
+    L = eng.layout
+    slots = sorted({eng.idxs[q] for q in range(info["rotation"])}) if info["rotation"] else list(range(info["narrays"]))
+    ok, nbytes, first_bad = True, 0, None
+    single = None
+    if rank == 0:
+        gdims = (nx, ny, ns * world) if info["ndims"] == 3 else (nx, ny * world, 1)
+        single = SlabEngine(pkg, test, real, gdims[0], gdims[1], gdims[2], scalars)
+        single.fill_pattern()
+        single.run(niters)
+        torch.cuda.synchronize()
+        assert single.idxs == eng.idxs
+    for q in slots:
+        a, b = (L.own_lo - L.mem_lo) * eng.unit, (L.own_hi - L.mem_lo) * eng.unit
+        mine = eng.t[q][a:b].contiguous()
+        if rank == 0:
+            g = torch.empty(L.n * eng.unit, dtype=mine.dtype, device=mine.device)
+            g[: mine.numel()] = mine
+            reqs = []
+            for r in range(1, world):
+                lo, hi = L.n * r // world * eng.unit, L.n * (r + 1) // world * eng.unit
+                reqs.append(dist.irecv(g[lo:hi], src=r))
+            for rq in reqs:
+                rq.wait()
+            torch.cuda.synchronize()
+            same = torch.equal(g.view(torch.int32 if real == "float" else torch.int64),
+                               single.t[q].view(torch.int32 if real == "float" else torch.int64))
+            nbytes += g.numel() * g.element_size()
+            if not same and first_bad is None:
+                first_bad = q
+            ok = ok and same
+            del g
+        else:
+            dist.send(mine, dst=0)
+    dist.barrier()
+    eng.close()
+    if single is not None:
+        single.close()
+    if rank != 0:
+        return None
+    res = {"multi_eq_single": bool(ok), "bytes_compared": int(nbytes), "test": test, "real": real,
+           "global_grid": f"{nx}x{ny}x{ns * world}" if info["ndims"] == 3 else f"{nx}x{ny * world}",
+           "niters": niters, "ranks": world, "halo": halo, "slots": slots}
+    if first_bad is not None:
+        res["first_bad_slot"] = first_bad
+    return res
+
+
 def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3, cpu_fn=None):
     """GLUP/s and fraction of the HBM roofline for every test, float and double, on cuda:0."""
     import torch
@@ -517,9 +608,9 @@ def suite_table(pkg, peak_gbs, full, scalars, niters=10, reps=3, cpu_fn=None):
 
 
 def matmul_table(pkg, n=8192, reps=3):
-    """TFLOP/s of the matmul test (C += A*B, n^3, BASELINE configs[4]) through b200_sweep_loop: the
-    hand-written tensor-core kernels, and the cuBLAS baseline (B200_MATMUL=cublas) beside them."""
-    import os
+    """TFLOP/s of the matmul test (C += A*B, n^3, BASELINE configs[4]) through b200_sweep_loop: the hand-written
+    tensor-core kernels; beside them cuBLAS on the same operands, called through torch (addmm_ -- a library baseline timed
+    in the bench only; the product library has no library-GEMM path)."""
     import torch
     rows = []
     stream = torch.cuda.current_stream().cuda_stream
@@ -528,18 +619,24 @@ def matmul_table(pkg, n=8192, reps=3):
             A = torch.rand(n * n, device="cuda", dtype=dt) * 2 - 1
             B = torch.rand(n * n, device="cuda", dtype=dt) * 2 - 1
             row = {"test": "matmul", "real": real, "size": f"{n}x{n}x{n}", "regs": pkg.kernel_info("matmul", real)["regs"]}
+            if dt == torch.float32:
+                torch.backends.cuda.matmul.allow_tf32 = False          # SGEMM, FP32 accuracy: the like-for-like baseline
             for mode in ("tensor", "cublas"):
-                if mode == "cublas":
-                    os.environ["B200_MATMUL"] = "cublas"
-                else:
-                    os.environ.pop("B200_MATMUL", None)
                 Cm = torch.zeros(n * n, device="cuda", dtype=dt)
                 ptrs = [A.data_ptr(), B.data_ptr(), Cm.data_ptr()]
-                pkg.capi.sweep_loop("matmul", real, n, n, n, [], ptrs, 1, stream=stream)
+                # column-major C(nx,ns) += A(nx,ny) B(ny,ns)  ==  row-major C^T += B^T A^T
+                At, Bt, Ct = A.view(n, n), B.view(n, n), Cm.view(n, n)
+                if mode == "tensor":
+                    run = lambda k: pkg.capi.sweep_loop("matmul", real, n, n, n, [], ptrs, k, stream=stream)   # noqa: E731
+                else:
+                    def run(k):
+                        for _ in range(k):
+                            Ct.addmm_(Bt, At)
+                run(1)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                pkg.capi.sweep_loop("matmul", real, n, n, n, [], ptrs, reps, stream=stream)
+                run(reps)
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / reps
@@ -553,6 +650,4 @@ def matmul_table(pkg, n=8192, reps=3):
         except Exception as e:
             rows.append({"test": "matmul", "real": real, "error": str(e)[:200]})
             torch.cuda.synchronize()
-        finally:
-            os.environ.pop("B200_MATMUL", None)
     return rows

@@ -28,3 +28,19 @@ def oracle():
 def oracle_strict():
     from oracle_util import Oracle
     return Oracle("strict")
+
+
+def _gpu_hardware_present() -> bool:
+    """A CUDA device node exists.  Deliberately NOT a check of the product library: on a GPU box a library that fails to
+    load must FAIL the gpu tests loudly, never skip them."""
+    import glob
+    return bool(glob.glob("/dev/nvidia[0-9]*"))
+
+
+def pytest_collection_modifyitems(config, items):
+    if _gpu_hardware_present():
+        return
+    skip = pytest.mark.skip(reason="no NVIDIA device on this machine (gpu tests run on the B200 box: pytest -m gpu)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -96,3 +96,19 @@ def test_bad_arguments(pkg):
     assert lib.b200_get_test_info(99) is None or not lib.b200_get_test_info(99)
     assert lib.b200_sweep(None, None, None) == 1          # B200_ERR_ARG
     assert lib.b200_interior_points(99, 8, 8, 8) == 0
+
+
+def test_bench_interior_points_match_library(pkg):
+    """bench.py's reference arm computes interior points in Python (it must not map the product library): the table it
+    uses has to agree with b200_interior_points for every stencil."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for test in bench.INTERIOR:
+        for dims in ((512, 256, 256), (5, 5, 5), (3, 3, 3), (130, 37, 29)):
+            nd = pkg.test_info(test)["ndims"]
+            nx, ny, ns = dims
+            lib = pkg.interior_points(test, nx, ny * ns, 1) if nd == 2 else pkg.interior_points(test, nx, ny, ns)
+            assert bench.interior_points_py(test, nx, ny, ns) == lib, (test, dims)
+        assert bench.NARRAYS[test] == pkg.test_info(test)["narrays"]

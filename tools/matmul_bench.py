@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """tools/matmul_bench.py [n] -- TFLOP/s of the matmul test (C += A*B, n x n x n) through b200_sweep_loop:
-hand-written tensor-core kernels vs the cuBLAS baseline (B200_MATMUL=cublas), float and double."""
+hand-written tensor-core kernels vs the cuBLAS baseline (B200_MATMUL=cublas), float and double.
+Needs the diagnostics library: make -C kernelgen-perf-tests_b200/csrc diag; B200_LIB=kernelgen-perf-tests_b200/libb200stencil_diag.so"""
 import os
 import sys
 from pathlib import Path
