@@ -379,12 +379,12 @@ template <typename T, int TYF = 24> struct LapgsrbOp : NoTmaStore {
 // ------------------------------------------------------------------------------------------
 template <typename T> B200_DEV void cubic_weights(T t, T (&w)[4])
 {
-    // 8 multiplies + 3 adds for the four weights (two shared two-factor products) instead of 12 + 3:
-    // the weights are 39 -> 33 of the ~120 FP64 instructions per point of a pipe-bound kernel
-    const T sixth = (T)(1.0 / 6.0), half = (T)0.5;
+    // 7 multiply-class operations + 3 adds for the four weights instead of 12 + 3: the weights are 30 of the ~114 FP64
+    // instructions per point of a pipe-bound kernel.  s = t (t+1) / 6 and h = (t-1) (t+2) / 2 = 3 s - 1 (one FMA).
+    const T sixth = (T)(1.0 / 6.0);
     const T tm1 = t - (T)1, tp1 = t + (T)1, tp2 = t + (T)2;
     const T s = (sixth * t) * tp1;          // t (t+1) / 6
-    const T h = (half * tm1) * tp2;         // (t-1) (t+2) / 2
+    const T h = (T)3 * s - (T)1;            // (t-1) (t+2) / 2
     w[0] = s * tp2;
     w[1] = -(h * tp1);
     w[2] = h * t;
@@ -529,6 +529,90 @@ template <typename T, int R, int NCV = 256, int STG = 6, bool SPLIT = false> str
         }
         B200_UNROLL
         for (int q = 0; q < R; q++) ctx.template store<1>(row0 + q, o[q]);
+    }
+};
+
+// Outer-product form of the same stencil (round 2).  Why: on B200 a DFMA whose three source operands are
+// three distinct registers occupies the FP64 path of an SM sub-partition for 3 clk, not 2 (the register file delivers one
+// 64-bit operand per lane per clk; measured, tools/probes/regbank_probe.cu: 3.00 clk per warp instruction, 2.17 with one
+// operand held in the operand-reuse cache, DMUL / DADD 2.00).  The separable x-y-z form above is made of such DFMAs
+// (weight x window value + accumulator, all different) and ptxas finds a reusable operand for one in five.
+// Here the sums are re-ordered so that the work of one window row is a RANK-1 UPDATE:
+//     T[q][v][i] += wzy[q][v] * W[v + i]          q: point row, v: point in the vector, i = 0..3, W: the row's window
+// with wzy = wc[kk] * wb[jj] formed once per (plane, row).  All the FMAs of a row are independent (sixteen accumulators per
+// point row pair), consecutive ones share either the weight or the window value, and the x weights are applied once at
+// the very end: out = sum_i wa[i] * T[i].  Same 84 multiply-adds per point (64 + 16 products wzy + 4), and the wa weights
+// are not live during the march (they are computed at the end from a).  Re-associated with respect to TricubicOp
+// (z and y before x): covered by the stated tolerance, not bit-identical to the other forms.
+template <typename T, int R, int NCV = 256, int STG = 8, bool SPLIT = true, int TXV = 128> struct TricubicOuterOp : NoTmaStore {
+    using real = T;
+    static constexpr int NC = NCV;
+    static constexpr int TX = TXV, TY = R * (NC / (TX / (16 / (int)sizeof(T)))), STAGES = STG, HOLD = 3, WARM = 3, PERIOD = 1;
+    static constexpr bool STREAM_OUT = false;
+    static constexpr int NSTAGED = 4;
+    static constexpr StagedSpec spec(int a)
+    {
+        return a == 0 ? StagedSpec{0, 1, 1, 2, 2, 1} : StagedSpec{a + 1, 0, 0, 0, 0, 0};
+    }
+    static constexpr bool transient(int a) { return SPLIT && a > 0; }
+    using G = Geo<TricubicOuterOp>;
+    static constexpr int V = G::V;
+    static_assert(G::CPT == R, "R adjacent rows per thread");
+    struct State { };
+    B200_DEV TricubicOuterOp(const StreamParams&) {}
+    template <class C> B200_DEV void pre(const C&, State&) {}
+    template <int PH, class C> B200_DEV void step(const C& ctx, State&)
+    {
+        if (ctx.rel < 0) return;
+        constexpr int BW = G::bw(0);
+        const int row0 = R * ctx.ty;
+        T av[R][V], wb[R][V][4], wc[R][V][4], acc[R][V][4];
+        B200_UNROLL
+        for (int q = 0; q < R; q++) {
+            const VReg<T> va = ldv(ctx.template tile<1>(row0 + q)), vb = ldv(ctx.template tile<2>(row0 + q)),
+                          vc = ldv(ctx.template tile<3>(row0 + q));
+            B200_UNROLL
+            for (int v = 0; v < V; v++) {
+                av[q][v] = va[v];
+                cubic_weights(vb[v], wb[q][v]);
+                cubic_weights(vc[v], wc[q][v]);
+            }
+        }
+        B200_UNROLL
+        for (int kk = 0; kk < 4; kk++) {
+            const T* p = ctx.template tile<0>(row0, 3 - kk);        // u0 plane s+kk-1, first owned row
+            B200_UNROLL
+            for (int r = 0; r < R + 3; r++) {                       // window row row0 - 1 + r
+                Window<1, 2, T> w;
+                w.load(p + (r - 1) * BW);
+                B200_UNROLL
+                for (int q = 0; q < R; q++) {
+                    const int jj = r - q;                           // this window row is row jj of point row q
+                    if (jj >= 0 && jj <= 3) {
+                        B200_UNROLL
+                        for (int v = 0; v < V; v++) {
+                            const T wzy = wc[q][v][kk] * wb[q][v][jj];
+                            B200_UNROLL
+                            for (int i = 0; i < 4; i++) {
+                                if (kk == 0 && jj == 0) acc[q][v][i] = wzy * w.w[v + i];
+                                else acc[q][v][i] = wzy * w.w[v + i] + acc[q][v][i];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        B200_UNROLL
+        for (int q = 0; q < R; q++) {
+            T o[V];
+            B200_UNROLL
+            for (int v = 0; v < V; v++) {
+                T wa[4];
+                cubic_weights(av[q][v], wa);
+                o[v] = ((wa[0] * acc[q][v][0] + wa[1] * acc[q][v][1]) + wa[2] * acc[q][v][2]) + wa[3] * acc[q][v][3];
+            }
+            ctx.template store<1>(row0 + q, o);
+        }
     }
 };
 

@@ -306,26 +306,34 @@ def test_async_contexts_match_sync(pkg, oracle, test, real, dims):
 
 
 def test_tricubic_row_variants():
-    """Every form of the tricubic kernel (b200_ops3d.cuh: 1 = TricubicOp, one row per thread; 2 = TricubicRowsOp<2>,
-    two adjacent rows per thread, 8 warps; 3 = the same with 10 warps and a 5-stage ring; 4 = 8 warps with a, b, c in
-    the engine's transient ring and 8 stages of u0) against the oracle, whichever is the default.  The library reads
-    B200_TRICUBIC_ROWS once per process, so each form runs in its own interpreter
-    (tests/tricubic_variant_check.py: tricubic + tricubic2, both precisions, ragged / odd / multi-tile sizes)."""
+    """Every form of the tricubic kernel that was measured on the way to the product form (k_tricubic.cu: 1-6 the
+    separable x-y-z forms, 7-10 the outer-product forms) against the oracle.  They live in the DIAGNOSTICS library
+    (libb200stencil_diag.so, B200_TRICUBIC_ROWS); the product library holds form 7 only and ignores the variable -- it is
+    run too ("0").  Each form runs in its own interpreter (tests/tricubic_variant_check.py: tricubic + tricubic2, both
+    precisions, ragged / odd / multi-tile sizes)."""
     import json
     import os
     import subprocess
     import sys
+    root = Path(__file__).resolve().parent.parent
+    diag = root / "kernelgen-perf-tests_b200" / "libb200stencil_diag.so"
+    assert diag.exists(), "diagnostics library missing: make -C kernelgen-perf-tests_b200/csrc diag (build() does it)"
     out = {}
-    for rows in ("1", "2", "3", "4"):
+    for rows in ("0", "1", "2", "4", "6", "7", "8", "9"):
         env = dict(os.environ, B200_TRICUBIC_ROWS=rows)
+        if rows != "0":
+            env["B200_LIB"] = str(diag)
+        else:
+            env.pop("B200_LIB", None)
         p = subprocess.run([sys.executable, str(Path(__file__).resolve().parent / "tricubic_variant_check.py")],
                            capture_output=True, text=True, env=env, timeout=900)
         assert p.returncode == 0, f"rows={rows}: {p.stdout[-2000:]} {p.stderr[-2000:]}"
         out[rows] = json.loads(p.stdout.strip().splitlines()[-1])
         for real in ("float", "double"):
             assert out[rows]["worst"][real] <= TOL[real], out[rows]
-    # same per-point arithmetic in the same order: reported, not required (the compiler is free to contract differently)
-    print("tricubic forms bit-identical:", len({o["sha"] for o in out.values()}) == 1, out)
+    # the product library runs form 7: same bytes as the diagnostics library's form 7
+    assert out["0"]["sha"] == out["7"]["sha"]
+    assert len({out[r]["sha"] for r in ("1", "2", "4", "6")}) == 1 and len({out[r]["sha"] for r in ("7", "8", "9")}) == 1
 
 
 @pytest.mark.parametrize("real", ["float", "double"])
