@@ -60,11 +60,26 @@ $t: \$(B200_SRCS) \$(B200_PKG)/drivers/kg_init.h \$(B200_PKG)/libb200stencil.so
 clean:
 	\$(SILENT)rm -rf *.o $t
 
+# the measured HBM ceiling of this pool (driver-written MEASURED_PEAKS.json), for the "% of the HBM roofline" figure
+B200_HBM_GBS ?= \$(shell sed -n 's/.*"hbm_gbs": *\([0-9.]*\).*/\1/p' \$(B200_ROOT)/MEASURED_PEAKS.json 2>/dev/null)
+export B200_HBM_GBS
+
 test: $t
 	\$(SILENT)./\$< $RUNARGS
 
+# like <test>/cuda/makefile:54-66 of the suite: check = memory checker, roofline = profiler metrics of the kernel
+SMALLARGS = 64 32 $( [ "$RUNARGS" = '$(NX) $(NY) $(NS) $(NT)' ] && echo 32 ) 2
 check: $t
-	\$(SILENT)compute-sanitizer --tool memcheck ./\$< 64 32 $( [ "$RUNARGS" = '$(NX) $(NY) $(NS) $(NT)' ] && echo 32 ) 2
+	\$(SILENT)compute-sanitizer --tool memcheck --error-exitcode 1 ./\$< \$(SMALLARGS)
+
+racecheck: $t
+	\$(SILENT)compute-sanitizer --tool racecheck --error-exitcode 1 ./\$< \$(SMALLARGS)
+
+synccheck: $t
+	\$(SILENT)compute-sanitizer --tool synccheck --error-exitcode 1 ./\$< \$(SMALLARGS)
+
+roofline: $t
+	\$(SILENT)ncu --clock-control none -c 1 -s 2 --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_fp64.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,smsp__sass_thread_inst_executed_op_ffma_pred_on.sum ./\$< $RUNARGS
 MK
 done
 
@@ -94,8 +109,16 @@ test.b200: $(TARGETS_B200)
 MK
 fi
 
-# benchmark: treat b200 like the cuda targets (kernel file, PROFILING_FNAME, t_krn, nreg_krn)
+# benchmark: treat b200 like the cuda targets (kernel file, PROFILING_FNAME, t_krn, nreg_krn) ...
 if ! grep -q 'b200' "$SUITE/benchmark"; then
     sed -i 's/(\$target =~ m\/\^cuda\.\*\$\/)/(($target =~ m\/^cuda.*$\/) or ($target eq "b200"))/g' "$SUITE/benchmark"
+    # ... and append two columns to its table, GLUP/s and % of the HBM roofline, parsed from the line the
+    # b200 driver prints ("b200: 1 GPU(s), X GLUP/s, Y GB/s algorithmic ..., Z % of the HBM roofline").  Other targets: N/A.
+    # mktable / mkchart read the "Data for table" / "Times for chart" blocks, which keep their format.
+    perl -0pi -e '
+        s/(\tprint_field\(\$final_mean\);\n)/$1\tprint_field(find_average(\$output, "", qr{b200:\\s\\d+\\sGPU\\(s\\),\\s([-+]?[0-9]*\\.?[0-9]+([eE][-+]?[0-9]+)?)\\sGLUP\/s}));\n\tprint_field(find_average(\$output, "", qr{,\\s([-+]?[0-9]*\\.?[0-9]+([eE][-+]?[0-9]+)?)\\s%\\sof\\sthe\\sHBM\\sroofline}));\n/;
+        s/\| %8s \|\\n",\n(\t\t"test", "target", "i_mean", "t_init", "t_alloc", "t_load", "t_comp",\n\t\t"t_krn", "nreg_krn", "t_save", "t_free", "f_mean")\);/| %8s | %8s | %8s |\\n",\n$1, "GLUP\/s", "%roof");/g;
+        s/my\(\$table_width\) = 148;/my(\$table_width) = 170;/;
+    ' "$SUITE/benchmark"
 fi
 echo "b200 target installed into $SUITE (library root: $B200_ROOT)"

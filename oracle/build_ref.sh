@@ -77,5 +77,14 @@ if command -v nvcc >/dev/null 2>&1; then
 fi
 
 grep -m1 '^flags' /proc/cpuinfo | cut -d: -f2 > "$OUT/build_host_flags.txt"
-rm -rf "$OUT/obj"
+rm -rf "$OUT/obj" "$OUT/obj_cuda"
 echo "oracle/_ref complete"
+
+# A writable checkout of the whole suite for the `benchmark`-on-the-GPU test (tests/test_gpu_benchmark.py): the Perl
+# scripts, makefiles and test sources the real `./benchmark <nx> <ny> <ns> <nt> <nruns> b200 gcc` needs on the GPU box.
+# Staged under oracle/_ref (git-ignored: never committed), it travels with the snapshot like the other _ref artefacts.
+rm -rf "$OUT/suite"
+mkdir -p "$OUT/suite"
+( cd "$REF" && tar --exclude=.git -cf - . ) | ( cd "$OUT/suite" && tar -xf - )
+chmod -R u+w "$OUT/suite"
+echo "staged $OUT/suite"

@@ -83,9 +83,11 @@ def test_parallel_init_same_inputs(test, real):
 
 
 def test_pinned_host_arrays_same_result():
-    """B200_PINNED_HOST=1 (page-locked host arrays instead of memalign): same means, load/save lines still there."""
-    a = parse_like_benchmark(run_driver("wave13pt", "double", [96, 40, 48, 3]), "wave13pt")
-    b = parse_like_benchmark(run_driver("wave13pt", "double", [96, 40, 48, 3], env={"B200_PINNED_HOST": "1"}), "wave13pt")
+    """Page-locked host arrays (the default) vs B200_PINNED_HOST=0 (memalign, as in the reference): same means, every
+    timing line still there, init time reported in both."""
+    a = parse_like_benchmark(run_driver("wave13pt", "double", [96, 40, 48, 3], env={"B200_PINNED_HOST": "0"}), "wave13pt")
+    b = parse_like_benchmark(run_driver("wave13pt", "double", [96, 40, 48, 3]), "wave13pt")
+    assert a["t_init"] is not None and b["t_init"] is not None and b["t_init"] > 0
     assert "%f" % a["i_mean"] == "%f" % b["i_mean"] and "%f" % a["f_mean"] == "%f" % b["f_mean"]
     assert b["t_load"] is not None and b["t_save"] is not None
 

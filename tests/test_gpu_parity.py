@@ -79,6 +79,22 @@ def test_golden_fixtures(ctx, pkg, test, real):
     assert stats["launches"] == nt - pairs          # a fused two-sweep pass is one launch
 
 
+@pytest.mark.parametrize("real", ["float", "double"])
+@pytest.mark.parametrize("test", ["jacobi", "sincos"])
+def test_golden_fixtures_fortran_tests(ctx, test, real):
+    """jacobi and sincos are Fortran in the reference (no gfortran in the build container): their fixtures hold the outputs
+    of the reference's DECLARATIVE definitions (jacobi/jacobi.stc:1-13, sincos/sincos.stc) evaluated by tests/stc_eval.py
+    (generator: tests/golden/make_golden_stc.py), on inputs drawn in the reference drivers' rand() order."""
+    fx = np.load(GOLDEN_DIR / f"{test}_{real}.npz")
+    nx, ny, ns, nt = [int(v) for v in fx["dims"]]
+    scalars = [float(v) for v in fx["scalars"]]
+    n = len([k for k in fx.files if k.startswith("in")])
+    inputs = [fx[f"in{q}"] for q in range(n)]
+    slot, got, stats = gpu_run(ctx, test, real, nx, ny, ns, nt, scalars, inputs)
+    want = [fx[f"stc{q}"] if f"stc{q}" in fx.files else fx[f"in{q}"] for q in range(n)]
+    check(test, real, nx, ny, ns, nt, scalars, inputs, got, want)
+
+
 SIZES_3D = [(128, 20, 12), (130, 37, 29), (63, 31, 29), (260, 19, 11), (16, 5, 5), (5, 5, 5)]
 SIZES_2D = [(128, 70, 1), (130, 517, 1), (63, 301, 1), (512, 300, 1), (5, 5, 1)]
 

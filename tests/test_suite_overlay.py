@@ -42,8 +42,11 @@ def test_overlay_install_build_and_benchmark(tmp_path, pkg):
     subprocess.run(["make", "-s", "laplacian.b200", "laplacian.gcc", "gameoflife.b200", "gameoflife.gcc", "matmul.b200"],
                    cwd=suite, check=True, capture_output=True)
     assert (suite / "laplacian" / "b200" / "laplacian").exists()
+    # B200_PINNED_HOST=0: memalign host arrays as in the reference, so that without a GPU the driver still gets as far as
+    # the "initial mean" line before b200_init refuses (the default page-locks the arrays, which needs the device first)
+    import os
     out = subprocess.run(["./benchmark", "16", "8", "8", "1", "1", "b200", "gcc"], cwd=suite,
-                         capture_output=True, text=True).stdout
+                         capture_output=True, text=True, env=dict(os.environ, B200_PINNED_HOST="0")).stdout
     assert "Found test laplacian" in out
     rows = {}
     for line in out.splitlines():
