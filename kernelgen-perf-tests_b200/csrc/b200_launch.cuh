@@ -79,6 +79,41 @@ int launch_variant(const StreamParams& P, const TensorMaps& M, const OutMaps& OM
     const long long items = (long long)tiles_xy * Q.nzc;
     if (items > 0x7fffffffLL) { set_error("grid too large"); return B200_ERR_ARG; }
     Q.nitems = (int)items;
+    if constexpr (PUSH) {
+        // Which units of the split dimension (z-chunks / tile rows) take part in the neighbour ordering: those that read a
+        // ghost plane of a staged input or store a plane that is pushed to a neighbour.  They are walked first (decode_item).
+        int zlo = 0, zhi = 0, ylo_h = 0, yhi_h = 0;
+        for (int a = 0; a < Op::NSTAGED; a++) {
+            zlo = Op::spec(a).zlo > zlo ? Op::spec(a).zlo : zlo;
+            zhi = Op::spec(a).lead > zhi ? Op::spec(a).lead : zhi;
+            ylo_h = Op::spec(a).ylo > ylo_h ? Op::spec(a).ylo : ylo_h;
+            yhi_h = Op::spec(a).yhi > yhi_h ? Op::spec(a).yhi : yhi_h;
+        }
+        const bool planes = Q.push_dim == 2;
+        const int n = planes ? Q.ns : Q.ny;                                  // local extent of the split dimension
+        const int o0 = planes ? Q.z0 : Q.ylo, o1 = planes ? Q.z1 : Q.yhi;    // output range
+        const int len = planes ? Q.zc_len : tile_py<Op>();
+        const int rlo = planes ? zlo : ylo_h, rhi = planes ? zhi : yhi_h;    // reach below / above an output unit
+        Q.split_n = planes ? Q.nzc : Q.nty;
+        Q.split_stride = planes ? tiles_xy : Q.ntx;
+        // ghost units: everything outside the owned output range on a side that has a neighbour
+        const int glo_end = Q.wait_flag[0] || Q.push_lo ? o0 : 0;            // ghost planes below: [0, o0)
+        const int ghi_beg = Q.wait_flag[1] || Q.push_hi ? o1 : n;            // ghost planes above: [o1, n)
+        auto is_end_unit = [&](int u) {
+            const int a = o0 + u * len, b = (a + len < o1) ? a + len : o1;   // output range of the unit
+            if (a - rlo < glo_end || b + rhi > ghi_beg) return true;          // reads a ghost plane
+            if (Q.push_lo && a < Q.push_lo_src + Q.push_lo_cnt && b > Q.push_lo_src) return true;
+            if (Q.push_hi && a < Q.push_hi_src + Q.push_hi_cnt && b > Q.push_hi_src) return true;
+            return false;
+        };
+        Q.e_lo = 0;
+        while (Q.e_lo < Q.split_n && is_end_unit(Q.e_lo)) Q.e_lo++;
+        Q.e_hi = 0;
+        while (Q.e_lo + Q.e_hi < Q.split_n && is_end_unit(Q.split_n - 1 - Q.e_hi)) Q.e_hi++;
+        for (int u = Q.e_lo; u < Q.split_n - Q.e_hi; u++)
+            if (is_end_unit(u)) { Q.e_lo = Q.split_n; Q.e_hi = 0; break; }    // cannot happen for a contiguous slab: order everything
+        Q.end_items = (Q.e_lo + Q.e_hi) * Q.split_stride;
+    }
     const int grid = (int)(items < grid_cap ? items : grid_cap);
     stream_kernel<Op, PUSH, TS><<<grid, G::NTHREADS, G::SMEM_BYTES, stream>>>(Q, M, OM);
     B200_CUDA(cudaGetLastError());

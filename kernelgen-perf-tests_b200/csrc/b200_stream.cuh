@@ -82,8 +82,15 @@ struct StreamParams {
     unsigned long long wait_value;
     unsigned long long* signal_flag[2];
     unsigned long long signal_value;
-    unsigned int* done_counter;     // per-device CTA completion counter (library-owned, self-resetting)
+    unsigned int* done_counter;     // per-device completion counter of the END items (library-owned, self-resetting)
     int reverse;                    // 1: walk the items in reverse order (serpentine sweeps)
+    // PUSH launches walk the "end" units of the split dimension first (z-chunks for the 3D tests, tile rows for the 2D
+    // tests: the e_lo lowest and e_hi highest of split_n units, split_stride items each).  Only those items read ghost
+    // planes or push planes to a neighbour, so only they take part in the neighbour ordering: the producer waits for the
+    // neighbours' flags before the first of them, and the flags are published when the last of them has completed --
+    // early in the sweep, long before a neighbour's next sweep asks for them (was: every CTA spun at kernel start on a flag
+    // the neighbour's LAST CTA released, so every sweep inherited the slowest neighbour's tail).
+    int split_n, split_stride, e_lo, e_hi, end_items;
 };
 
 struct alignas(64) TensorMaps {
@@ -453,7 +460,7 @@ template <class Op, int A> struct ProducerIssue {
     }
 };
 
-struct ItemCoords { int X0, Y0, za, zb; };
+struct ItemCoords { int X0, Y0, za, zb; bool is_end; };
 
 // tile pitch / origin: an Op may declare PX, PY, OX, OY (fused two-sweep Ops); default = the tile itself
 template <class Op, class = void> struct TileGrid { static constexpr int PX = Op::TX, PY = Op::TY, OX = 0, OY = 0; };
@@ -463,14 +470,31 @@ template <class Op> constexpr int tile_py() { return TileGrid<Op>::PY; }
 template <class Op> constexpr int tile_ox() { return TileGrid<Op>::OX; }
 template <class Op> constexpr int tile_oy() { return TileGrid<Op>::OY; }
 
-template <class Op> B200_DEV ItemCoords decode_item(const StreamParams& P, int item)
+template <class Op, bool PUSH> B200_DEV ItemCoords decode_item(const StreamParams& P, int item)
 {
     const int tiles_xy = P.ntx * P.nty;
-    if (P.reverse) item = P.nitems - 1 - item;
+    ItemCoords c;
+    c.is_end = false;
+    if constexpr (PUSH) {
+        // ends first: position u' in the walk -> unit u of the split dimension
+        const int up = item / P.split_stride;
+        int w = item - up * P.split_stride;
+        int u;
+        if (up < P.e_lo) u = up;
+        else if (up < P.e_lo + P.e_hi) u = P.split_n - P.e_hi + (up - P.e_lo);
+        else {
+            const int m = up - P.e_lo - P.e_hi, nm = P.split_n - P.e_lo - P.e_hi;
+            u = P.e_lo + (P.reverse ? nm - 1 - m : m);
+            if (P.reverse) w = P.split_stride - 1 - w;
+        }
+        c.is_end = up < P.e_lo + P.e_hi;
+        item = u * P.split_stride + w;
+    } else {
+        if (P.reverse) item = P.nitems - 1 - item;
+    }
     const int zc = item / tiles_xy;
     const int t = item - zc * tiles_xy;
     const int tyi = t / P.ntx, txi = t - tyi * P.ntx;
-    ItemCoords c;
     c.X0 = txi * tile_px<Op>() + tile_ox<Op>();        // multiples of V: vectors stay 16-byte aligned
     c.Y0 = P.ylo + tyi * tile_py<Op>() + tile_oy<Op>();
     c.za = P.z0 + zc * P.zc_len;
@@ -519,24 +543,6 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
             }
         }
         mbar_fence_init();
-        if constexpr (PUSH) {
-            // the neighbours' previous sweep must have finished pushing our ghosts (and reading theirs)
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const unsigned long long* f = P.wait_flag[i];
-                if (f) {
-                    unsigned long long cur, t0, now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                    for (;;) {
-                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(f) : "memory");
-                        if (cur >= P.wait_value) break;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                        if (now - t0 > 20000000000ull) __trap();      // a neighbour died: fail, do not hang
-                        __nanosleep(100);
-                    }
-                }
-            }
-        }
     }
     __syncthreads();
 
@@ -548,8 +554,36 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
             for (int a = 0; a < Op::NSTAGED; a++) tma_prefetch_desc(&M.m[a]);
         }
         uint32_t g = 0;
+        bool ordered = false;
         for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-            const ItemCoords c = decode_item<Op>(P, item);
+            const ItemCoords c = decode_item<Op, PUSH>(P, item);
+            if constexpr (PUSH) {
+                // An end item reads ghost planes (the neighbours' previous sweep must have pushed them) and its consumers
+                // push into the neighbours' ghost planes (the neighbours must have finished reading the values they replace,
+                // which they did in their previous sweep's end items): both are what the neighbours' flags >= wait_value say.
+                // The consumers cannot start the item before its first stage is full, i.e. before this wait is over.
+                if (c.is_end && !ordered) {
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const unsigned long long* f = P.wait_flag[i];
+                            if (f) {
+                                unsigned long long cur, t0, now;
+                                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                                for (;;) {
+                                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(f) : "memory");
+                                    if (cur >= P.wait_value) break;
+                                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                    if (now - t0 > 20000000000ull) __trap();      // a neighbour died: fail, do not hang
+                                    __nanosleep(100);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp(P.use_tma ? 1u : 0xffffffffu);
+                    ordered = true;
+                }
+            }
             for (int s = c.za - Op::WARM; s < c.zb; ++s, ++g) {
                 const uint32_t st = g % S, ph = (g / S) & 1u;
                 mbar_wait(&empty[st], ph ^ 1u);
@@ -575,7 +609,7 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
             if (lane != 0) goto finish;
             uint32_t og = 0;
             for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-                const ItemCoords c = decode_item<Op>(P, item);
+                const ItemCoords c = decode_item<Op, PUSH>(P, item);
                 for (int s = c.za - Op::WARM; s < c.zb; ++s) {
                     if (!G::emits(s, c.za, c.zb)) continue;
                     const uint32_t ob = og & 1u;
@@ -603,7 +637,7 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
         uint32_t st = 0, ph = 0, rel_st = (uint32_t)(S - Op::HOLD) % S;    // ring stage / parity of this step; stage to hand back
         uint32_t g = 0, og = 0;
         for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-            const ItemCoords c = decode_item<Op>(P, item);
+            const ItemCoords c = decode_item<Op, PUSH>(P, item);
             ctx.begin_item(c.X0, c.Y0);
             ctx.zb = c.zb;
             int local = 0, phase = 0;
@@ -664,25 +698,29 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
                 if (lane == 0)
                     for (int h = held; h >= 1; h--) mbar_arrive(&empty[(g - (uint32_t)h) % S]);
             }
-        }
-    }
-finish:
-    if constexpr (PUSH) {
-        // last CTA of the grid tells the neighbours that this sweep (and its halo push) is complete
-        __syncthreads();
-        if (tid == 0 && (P.signal_flag[0] || P.signal_flag[1])) {
-            __threadfence_system();
-            const unsigned int prev = atomicAdd(P.done_counter, 1u);
-            if (prev == gridDim.x - 1) {
-                *P.done_counter = 0u;
-                __threadfence_system();
+            if constexpr (PUSH) {
+                // the last END item of the grid to complete tells the neighbours that this sweep's halo push is done and
+                // that their ghost planes of the previous sweep have been read
+                if (c.is_end && (P.signal_flag[0] || P.signal_flag[1])) {
+                    asm volatile("bar.sync 2, %0;" ::"n"(G::NC) : "memory");       // every consumer warp has finished the item
+                    if (tid == 0) {
+                        __threadfence_system();
+                        const unsigned int prev = atomicAdd(P.done_counter, 1u);
+                        if (prev == (unsigned int)P.end_items - 1u) {
+                            *P.done_counter = 0u;
+                            __threadfence_system();
 #pragma unroll
-                for (int i = 0; i < 2; i++)
-                    if (P.signal_flag[i])
-                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.signal_flag[i]), "l"(P.signal_value) : "memory");
+                            for (int i = 0; i < 2; i++)
+                                if (P.signal_flag[i])
+                                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.signal_flag[i]), "l"(P.signal_value) : "memory");
+                        }
+                    }
+                }
             }
         }
     }
+finish:
+    return;
 }
 
 }  // namespace b200

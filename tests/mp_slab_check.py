@@ -27,6 +27,10 @@ CASES = [("laplacian", (34, 18, 13)), ("wave13pt", (32, 20, 17)), ("lapgsrb", (3
 SCAL = {"laplacian": [0.3, 0.1], "wave13pt": [0.6, -0.03, 0.09], "lapgsrb": [0.5, 0.03, 0.02, -0.01],
         "uxx1": [0.4, -0.2], "divergence": [0.6, -0.2, 0.5], "jacobi": [0.5, 0.1, 0.02],
         "gaussblur": [0.6, 0.2, 0.1, 0.05, 0.03, 0.01]}
+# nccl backend only: slabs large enough for several z-chunks / tile rows per CTA, so that the "ends first" walk of the halo-
+# pushing kernels (interior units take no part in the neighbour ordering) is exercised, not only one-item grids
+BIG_CASES = [("laplacian", (256, 96, 120)), ("wave13pt", (256, 60, 150)), ("lapgsrb", (128, 50, 90)), ("tricubic", (128, 40, 60)),
+             ("jacobi", (256, 2500, 1)), ("gaussblur", (384, 1500, 1)), ("gameoflife", (256, 1800, 1))]
 NT = 4
 
 
@@ -49,7 +53,7 @@ def main():
         dist.init_process_group("gloo")
     failures = []
     for real in ("double", "float"):
-        for test, (nx, ny, per_rank) in CASES:
+        for test, (nx, ny, per_rank) in CASES + (BIG_CASES if backend == "nccl" else []):
             info = pkg.test_info(test)
             sc = SCAL.get(test, [])
             split_local = per_rank if info["ndims"] == 3 else ny
