@@ -277,8 +277,7 @@ template <class Big, class Small> int launch_by_tile_policy(const HostArgs& a)
     if (pol == 1) {
         const b200_sweep_desc& d = *a.desc;
         const b200_test_info* ti = b200_get_test_info(d.test);
-        const bool whole = d.out_begin == 0 && d.out_end == 0 && !d.push_lo && !d.push_hi;   // slabs keep the default form
-        if (whole && ti->ndims == 3 &&
+        if (ti->ndims == 3 &&          // whole grids and z-slabs alike (the extents are those of the local array)
             decomposition_score<Small>(ti, d.nx, d.ny, d.ns, a.num_sms) >
                 SMALL_TILE_GAIN * decomposition_score<Big>(ti, d.nx, d.ny, d.ns, a.num_sms))
             return launch_stream<Small>(a);

@@ -336,42 +336,25 @@ template <class Op, bool PUSH, bool TS = false> struct Ctx : CtxTransient<Geo<Op
     // dplane: store into plane s + dplane instead (no halo push for those).
     template <int SLOT> B200_DEV void store(int row, const T (&val)[V], int dplane = 0) const
     {
-        if constexpr (Op::PRED_STORE && !PUSH && !(TS && G::out_q(SLOT) >= 0)) {
-            // the common case: branch-free
-            const unsigned off = idx0 + (unsigned)(row * P.nx);
-            put_pred(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val, row < rows_valid ? 1 : 0);
-            return;
-        }
-        if (row >= rows_valid || xmode == 0) return;
         const unsigned off = idx0 + (unsigned)(row * P.nx);
-        if constexpr (TS && G::out_q(SLOT) >= 0) {
-            if (xmode == 1) {
-                // whole vector inside the interior: into the staging tile, the store warp sends it with TMA
-                VReg<T> r;
-#pragma unroll
-                for (int v = 0; v < V; v++) r[v] = val[v];
-                T* dst = reinterpret_cast<T*>(ostage + G::out_q(SLOT) * G::OUT_TILE_BYTES) + (row * opitch + V * tx - oshift);
-                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(r.v);
-            } else {
-                put(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val);
-            }
+        if constexpr (Op::PRED_STORE && !(TS && G::out_q(SLOT) >= 0)) {
+            // the common case: branch-free
+            put_pred(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val, row < rows_valid ? 1 : 0);
         } else {
-            put(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val);
-        }
-        if constexpr (PUSH) {
-            // fused halo push: the same values also go to the neighbour GPU's ghost planes (rows for
-            // the 2D tests) through a peer-mapped pointer, i.e. over NVLink, while the sweep runs
-            if (SLOT == P.push_slot) {
-                const int coord = P.push_dim == 2 ? s : Y0 + row;
-                if (P.push_lo && coord >= P.push_lo_src && coord < P.push_lo_src + P.push_lo_cnt) {
-                    const long long d = coord - P.push_lo_src + P.push_lo_dst;
-                    T* base = reinterpret_cast<T*>(P.push_lo);
-                    put(P.push_dim == 2 ? base + d * P.nxny + off : base + d * P.nx + x, val);
-                }
-                if (P.push_hi && coord >= P.push_hi_src && coord < P.push_hi_src + P.push_hi_cnt) {
-                    const long long d = coord - P.push_hi_src + P.push_hi_dst;
-                    T* base = reinterpret_cast<T*>(P.push_hi);
-                    put(P.push_dim == 2 ? base + d * P.nxny + off : base + d * P.nx + x, val);
+            if (row < rows_valid && xmode != 0) {
+                if constexpr (TS && G::out_q(SLOT) >= 0) {
+                    if (xmode == 1) {
+                        // whole vector inside the interior: into the staging tile, the store warp sends it with TMA
+                        VReg<T> r;
+#pragma unroll
+                        for (int v = 0; v < V; v++) r[v] = val[v];
+                        T* dst = reinterpret_cast<T*>(ostage + G::out_q(SLOT) * G::OUT_TILE_BYTES) + (row * opitch + V * tx - oshift);
+                        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(r.v);
+                    } else {
+                        put(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val);
+                    }
+                } else {
+                    put(reinterpret_cast<T*>(P.arr[SLOT]) + (poff + dplane * P.nxny) + off, val);
                 }
             }
         }
@@ -500,6 +483,46 @@ template <class Op, bool PUSH> B200_DEV ItemCoords decode_item(const StreamParam
     c.za = P.z0 + zc * P.zc_len;
     c.zb = min(P.z1, c.za + P.zc_len);
     return c;
+}
+
+// Copies what one finished END item contributes to the neighbours' ghosts: for each side, the planes (3D tests) or rows
+// (2D tests) of the pushed output array that lie in both the item's box and the side's source range.
+template <class Op> B200_DEV void push_item(const StreamParams& P, const ItemCoords& c, int rows_valid, int tid)
+{
+    using T = typename Op::real;
+    using G = Geo<Op>;
+    constexpr int V = G::V;
+    const T* own = reinterpret_cast<const T*>(P.arr[P.push_slot]);
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+        T* peer = reinterpret_cast<T*>(side ? P.push_hi : P.push_lo);
+        if (!peer) continue;
+        const int src = side ? P.push_hi_src : P.push_lo_src, cnt = side ? P.push_hi_cnt : P.push_lo_cnt;
+        const int dst = side ? P.push_hi_dst : P.push_lo_dst;
+        // 3D: planes [p0, p1) x all valid tile rows; 2D: the one plane x rows [r0, r1)
+        int p0 = 0, p1 = 1, r0 = 0, r1 = rows_valid;
+        if (P.push_dim == 2) { p0 = max(src, c.za); p1 = min(src + cnt, c.zb); }
+        else { r0 = max(src - c.Y0, 0); r1 = min(src + cnt - c.Y0, rows_valid); }
+        if (p1 <= p0 || r1 <= r0) continue;
+        const int nrow = r1 - r0, per_plane = nrow * G::LX;
+#pragma unroll 1
+        for (int e = tid; e < (p1 - p0) * per_plane; e += G::NC) {
+            const int pl = e / per_plane, w = e - pl * per_plane;
+            const int row = r0 + w / G::LX, x = c.X0 + V * (w % G::LX);
+            if (x + V <= P.xlo || x >= P.xhi) continue;
+            const int y = c.Y0 + row, p = p0 + pl;
+            const long long from = P.push_dim == 2 ? (long long)p * P.nxny + (long long)y * P.nx + x : (long long)y * P.nx + x;
+            const long long to = P.push_dim == 2 ? (long long)(p - src + dst) * P.nxny + (long long)y * P.nx + x
+                                                 : (long long)(y - src + dst) * P.nx + x;
+            if (P.vec_ok && x >= P.xlo && x + V <= P.xhi) {
+                *reinterpret_cast<uint4*>(peer + to) = __ldcg(reinterpret_cast<const uint4*>(own + from));    // L2: written by other warps
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; v++)
+                    if (x + v >= P.xlo && x + v < P.xhi) peer[to + v] = __ldcg(own + from + v);
+            }
+        }
+    }
 }
 
 // One CTA per SM: 12 consumer warps + the producer warp.  The register file is split over the
@@ -633,7 +656,7 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
         // ------------------------------ consumer warps ------------------------------
         Op op(P);
         typename Op::State state;
-        Ctx<Op, PUSH, TS> ctx{{}, P, stages, extra, ostages, G::TX, 0, 0u, 0, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0, 0u, 0ll};
+        Ctx<Op, PUSH, TS> ctx{{}, P, stages, extra, ostages, G::TX, 0, 0u, 0, 0, 0, 0, 0, tid % G::LX, tid / G::LX, 0, 0, 0, 0, 0, 0u, 0ll};
         uint32_t st = 0, ph = 0, rel_st = (uint32_t)(S - Op::HOLD) % S;    // ring stage / parity of this step; stage to hand back
         uint32_t g = 0, og = 0;
         for (int item = blockIdx.x; item < P.nitems; item += gridDim.x) {
@@ -658,23 +681,7 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
                     }
                 }
                 mbar_wait(&full[st], ph);
-                if constexpr (PUSH) {
-                    // Only the steps that really produce a neighbour's ghost plane (rows, for the 2D tests) run the
-                    // variant with the halo-push code; every other step runs the single-GPU step (branch-free
-                    // stores, no push tests).  The two Ctx types have the same layout.
-                    bool push_now;
-                    if (P.push_dim == 2)
-                        push_now = (P.push_lo && s >= P.push_lo_src && s < P.push_lo_src + P.push_lo_cnt) ||
-                                   (P.push_hi && s >= P.push_hi_src && s < P.push_hi_src + P.push_hi_cnt);
-                    else
-                        push_now = (P.push_lo && c.Y0 < P.push_lo_src + P.push_lo_cnt && c.Y0 + G::TY > P.push_lo_src) ||
-                                   (P.push_hi && c.Y0 < P.push_hi_src + P.push_hi_cnt && c.Y0 + G::TY > P.push_hi_src);
-                    using CtxPlain = Ctx<Op, false, TS>;
-                    if (push_now) step_dispatch<Op, Ctx<Op, true, TS>>(op, ctx, state, phase);
-                    else step_dispatch<Op, CtxPlain>(op, reinterpret_cast<const CtxPlain&>(ctx), state, phase);
-                } else {
-                    step_dispatch<Op, Ctx<Op, PUSH, TS>>(op, ctx, state, phase);
-                }
+                step_dispatch<Op, Ctx<Op, PUSH, TS>>(op, ctx, state, phase);
                 if constexpr (TS) {
                     if (emit) {
                         fence_proxy_async_smem();
@@ -701,8 +708,19 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
             if constexpr (PUSH) {
                 // the last END item of the grid to complete tells the neighbours that this sweep's halo push is done and
                 // that their ghost planes of the previous sweep have been read
-                if (c.is_end && (P.signal_flag[0] || P.signal_flag[1])) {
+                if (c.is_end) {
                     asm volatile("bar.sync 2, %0;" ::"n"(G::NC) : "memory");       // every consumer warp has finished the item
+                    // Fused halo push: the part of the planes (3D) / rows (2D) a neighbour needs as ghosts that this item has
+                    // just written goes from this GPU's memory (still in L2) straight into the neighbour's ghost planes
+                    // through the peer-mapped pointer, over NVLink, while the other CTAs keep sweeping.  Done here, by all
+                    // consumer threads, and not inside Op::step(): a push inside the step costs every step registers and
+                    // instructions (measured, profiles/r2_push_variants.txt: two inlined step variants +20 % instructions;
+                    // one variant with the push behind a branch, inlined or as a cold call, +25-45 % time for the stencils
+                    // that sit at their register cap: lapgsrb, tricubic, gaussblur).
+                    push_item<Op>(P, c, ctx.rows_valid, tid);
+                    asm volatile("bar.sync 2, %0;" ::"n"(G::NC) : "memory");       // ... and has pushed its share
+                }
+                if (c.is_end && (P.signal_flag[0] || P.signal_flag[1])) {
                     if (tid == 0) {
                         __threadfence_system();
                         const unsigned int prev = atomicAdd(P.done_counter, 1u);
