@@ -234,6 +234,14 @@ int b200_host_free(void* ptr);
  * release at system scope); before the next sweep it waits (b200_wait spins on its own flag on
  * the device, acquire at system scope) -- no host round trip, no collective on the data path.
  * b200_wait traps after ~20 s instead of hanging. */
+/* b200_load_shell for a slab the CALLER owns (one process per GPU): copies the points outside the interior box from the host
+ * copy of the slab -- planes (3D) / rows (2D) [mem_lo, mem_hi) of a grid whose split dimension has split_n units, both
+ * pointers starting at unit mem_lo -- asynchronously on `stream`.  For the output buffers of a job
+ * (b200_slot_interior_dead): ghost planes need not travel either, the neighbours' first sweep pushes them.  Replaces the
+ * whole-array cudaMemcpy of laplacian/laplacian.c:257-258 for those arrays. */
+int b200_load_shell_slab(int test, int dtype, int nx, int ny, int split_n, int mem_lo, int mem_hi, void* dev_slab,
+                         const void* host_slab, void* stream);
+
 #define B200_IPC_HANDLE_BYTES 64
 int b200_device_alloc(void** ptr, size_t bytes);
 int b200_device_free(void* ptr);

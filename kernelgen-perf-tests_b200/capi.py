@@ -31,7 +31,7 @@ EXPORTS = ["b200_get_test_info", "b200_test_by_name", "b200_last_error", "b200_a
            "b200_launch_count", "b200_init", "b200_plan", "b200_alloc", "b200_load", "b200_run",
            "b200_slot_interior_dead", "b200_load_shell", "b200_result_slot", "b200_save", "b200_rewind", "b200_set_async", "b200_sync", "b200_free", "b200_destroy", "b200_host_alloc",
            "b200_host_free", "b200_device_alloc", "b200_device_free", "b200_ipc_export",
-           "b200_ipc_import", "b200_ipc_close", "b200_signal", "b200_wait"]
+           "b200_ipc_import", "b200_ipc_close", "b200_signal", "b200_wait", "b200_load_shell_slab"]
 IPC_HANDLE_BYTES = 64
 
 
@@ -117,6 +117,7 @@ def load() -> C.CDLL:
     L.b200_ipc_close.argtypes = [C.c_void_p]
     L.b200_signal.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p]
     L.b200_wait.argtypes = [C.c_void_p, C.c_ulonglong, C.c_void_p]
+    L.b200_load_shell_slab.argtypes = [C.c_int] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -265,6 +266,17 @@ def signal_flag(flag_ptr: int, value: int, stream: int = 0):
 
 def wait_flag(flag_ptr: int, value: int, stream: int = 0):
     _check(load().b200_wait(C.c_void_p(flag_ptr), value, C.c_void_p(stream)))
+
+
+def slot_interior_dead(test, slot: int) -> bool:
+    """b200_slot_interior_dead: the first sweep overwrites this array's interior before anything reads it."""
+    return bool(load().b200_slot_interior_dead(_tid(test), slot))
+
+
+def load_shell_slab(test, dtype, nx, ny, split_n, mem_lo, mem_hi, dev_ptr: int, host_ptr: int, stream: int = 0):
+    """b200_load_shell_slab: boundary shell of a caller-owned slab, host -> device, asynchronous on `stream`."""
+    _check(load().b200_load_shell_slab(_tid(test), _DT[dtype], nx, ny, split_n, mem_lo, mem_hi, C.c_void_p(dev_ptr),
+                                       C.c_void_p(host_ptr), C.c_void_p(stream)))
 
 
 class PinnedBuffer:

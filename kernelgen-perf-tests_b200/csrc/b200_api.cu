@@ -692,59 +692,81 @@ int b200_slot_interior_dead(int test, int slot)
     }
 }
 
-// Copies the points outside the interior box of the plan's test from `host` (a whole array) into the
-// slab buffers of `slot` (to_scratch: into the slabs' scratch buffers instead).
-static int upload_shell(b200_ctx* c, int slot, const void* host, bool to_scratch)
+// Copies the points outside the interior box of a test from a host slab into the device copy of the same slab: planes
+// (3D) / rows (2D) [mem_lo, mem_hi) of a grid whose split dimension has split_n units; `src` and `dst` both start at unit
+// mem_lo.  A few strided copies on `stream`.
+static int shell_copy(const b200_test_info* ti, size_t esz, int nx, int ny, int split_n, int mem_lo, int mem_hi,
+                      char* dst, const char* src, cudaStream_t stream)
 {
-    const b200_test_info* ti = b200_get_test_info(c->test);
-    const size_t esz = esz_of(c->dtype);
-    const int nx = c->nx, ny = c->ny;
     const bool d3 = ti->ndims == 3;
     const int lox = ti->lo[0], hix = ti->hi[0], loy = ti->lo[1], hiy = ti->hi[1];
     const int loz = d3 ? ti->lo[2] : 0, hiz = d3 ? ti->hi[2] : 0;
     const size_t row_b = (size_t)nx * esz, plane_b = row_b * (size_t)ny;
+    const int n_split = mem_hi - mem_lo;                   // planes (3D) / rows (2D) stored in the slab
+    const size_t rows = d3 ? (size_t)ny * n_split : (size_t)n_split;
+    if (rows == 0) return B200_OK;
+    const bool no_interior = nx <= lox + hix || (d3 && ny <= loy + hiy);
+    if (no_interior) {                                       // degenerate: everything is shell
+        B200_CUDA(cudaMemcpyAsync(dst, src, rows * row_b, cudaMemcpyHostToDevice, stream));
+        return B200_OK;
+    }
+    // (1) x edges of every row: the right edge of row r and the left edge of row r+1 are adjacent
+    if (lox + hix > 0) {
+        if (lox) B200_CUDA(cudaMemcpyAsync(dst, src, (size_t)lox * esz, cudaMemcpyHostToDevice, stream));
+        if (hix) B200_CUDA(cudaMemcpyAsync(dst + rows * row_b - (size_t)hix * esz, src + rows * row_b - (size_t)hix * esz,
+                                           (size_t)hix * esz, cudaMemcpyHostToDevice, stream));
+        if (rows > 1)
+            B200_CUDA(cudaMemcpy2DAsync(dst + row_b - (size_t)hix * esz, row_b, src + row_b - (size_t)hix * esz, row_b,
+                                        (size_t)(lox + hix) * esz, rows - 1, cudaMemcpyHostToDevice, stream));
+    }
+    // (2) whole rows / planes outside the interior in the split dimension (global coordinates)
+    const int glo = d3 ? loz : loy, ghi = split_n - (d3 ? hiz : hiy);         // interior [glo, ghi) of the split dim
+    const size_t unit_b = d3 ? plane_b : row_b;
+    int a0 = mem_lo, a1 = mem_hi < glo ? mem_hi : glo;                         // below the interior
+    if (a1 > a0) B200_CUDA(cudaMemcpyAsync(dst + (size_t)(a0 - mem_lo) * unit_b, src + (size_t)(a0 - mem_lo) * unit_b,
+                                           (size_t)(a1 - a0) * unit_b, cudaMemcpyHostToDevice, stream));
+    a0 = mem_lo > ghi ? mem_lo : ghi; a1 = mem_hi;                             // above the interior
+    if (a1 > a0) B200_CUDA(cudaMemcpyAsync(dst + (size_t)(a0 - mem_lo) * unit_b, src + (size_t)(a0 - mem_lo) * unit_b,
+                                           (size_t)(a1 - a0) * unit_b, cudaMemcpyHostToDevice, stream));
+    // (3) 3D: the y-shell rows of every plane
+    if (d3) {
+        if (loy) B200_CUDA(cudaMemcpy2DAsync(dst, plane_b, src, plane_b, (size_t)loy * row_b, n_split, cudaMemcpyHostToDevice, stream));
+        if (hiy) B200_CUDA(cudaMemcpy2DAsync(dst + plane_b - (size_t)hiy * row_b, plane_b, src + plane_b - (size_t)hiy * row_b, plane_b,
+                                             (size_t)hiy * row_b, n_split, cudaMemcpyHostToDevice, stream));
+    }
+    return B200_OK;
+}
+
+// Context form: `host` is a whole array; every slab takes its part (to_scratch: into the slabs' scratch buffers instead).
+static int upload_shell(b200_ctx* c, int slot, const void* host, bool to_scratch)
+{
+    const b200_test_info* ti = b200_get_test_info(c->test);
+    const size_t esz = esz_of(c->dtype);
     for (int g = 0; g < c->ngpus; g++) {
         b200_slab& s = c->slab[g];
         B200_CUDA(cudaSetDevice(s.dev));
         char* dst = (char*)(to_scratch ? s.scratch : s.arr[slot]);
         if (!dst) continue;
         const char* src = (const char*)host + c->unit * (size_t)s.mem_lo * esz;
-        const int n_split = s.mem_hi - s.mem_lo;               // planes (3D) / rows (2D) stored on this slab
-        const size_t rows = d3 ? (size_t)ny * n_split : (size_t)n_split;
-        if (rows == 0) continue;
-        const bool no_interior = nx <= lox + hix || (d3 && ny <= loy + hiy);
-        if (no_interior) {                                       // degenerate: everything is shell
-            B200_CUDA(cudaMemcpyAsync(dst, src, rows * row_b, cudaMemcpyHostToDevice, s.stream));
-            continue;
-        }
-        // (1) x edges of every row: the right edge of row r and the left edge of row r+1 are adjacent
-        if (lox + hix > 0) {
-            if (lox) B200_CUDA(cudaMemcpyAsync(dst, src, (size_t)lox * esz, cudaMemcpyHostToDevice, s.stream));
-            if (hix) B200_CUDA(cudaMemcpyAsync(dst + rows * row_b - (size_t)hix * esz, src + rows * row_b - (size_t)hix * esz,
-                                               (size_t)hix * esz, cudaMemcpyHostToDevice, s.stream));
-            if (rows > 1)
-                B200_CUDA(cudaMemcpy2DAsync(dst + row_b - (size_t)hix * esz, row_b, src + row_b - (size_t)hix * esz, row_b,
-                                            (size_t)(lox + hix) * esz, rows - 1, cudaMemcpyHostToDevice, s.stream));
-        }
-        // (2) whole rows / planes outside the interior in the split dimension (global coordinates)
-        const int glo = d3 ? loz : loy, ghi = c->split_n - (d3 ? hiz : hiy);   // interior [glo, ghi) of the split dim
-        const size_t unit_b = d3 ? plane_b : row_b;
-        int a0 = s.mem_lo, a1 = s.mem_hi < glo ? s.mem_hi : glo;                 // below the interior
-        if (a1 > a0) B200_CUDA(cudaMemcpyAsync(dst + (size_t)(a0 - s.mem_lo) * unit_b, src + (size_t)(a0 - s.mem_lo) * unit_b,
-                                               (size_t)(a1 - a0) * unit_b, cudaMemcpyHostToDevice, s.stream));
-        a0 = s.mem_lo > ghi ? s.mem_lo : ghi; a1 = s.mem_hi;                     // above the interior
-        if (a1 > a0) B200_CUDA(cudaMemcpyAsync(dst + (size_t)(a0 - s.mem_lo) * unit_b, src + (size_t)(a0 - s.mem_lo) * unit_b,
-                                               (size_t)(a1 - a0) * unit_b, cudaMemcpyHostToDevice, s.stream));
-        // (3) 3D: the y-shell rows of every plane
-        if (d3) {
-            if (loy) B200_CUDA(cudaMemcpy2DAsync(dst, plane_b, src, plane_b, (size_t)loy * row_b, n_split, cudaMemcpyHostToDevice, s.stream));
-            if (hiy) B200_CUDA(cudaMemcpy2DAsync(dst + plane_b - (size_t)hiy * row_b, plane_b, src + plane_b - (size_t)hiy * row_b, plane_b,
-                                                 (size_t)hiy * row_b, n_split, cudaMemcpyHostToDevice, s.stream));
-        }
+        if (int rc = shell_copy(ti, esz, c->nx, c->ny, c->split_n, s.mem_lo, s.mem_hi, dst, src, s.stream)) return rc;
     }
     if (int rc = sync_streams(c)) return rc;
     B200_CUDA(cudaSetDevice(c->slab[0].dev));
     return B200_OK;
+}
+
+// Stateless form for launchers that own the slab buffers (one process per GPU): see include/b200_stencil.h.
+int b200_load_shell_slab(int test, int dtype, int nx, int ny, int split_n, int mem_lo, int mem_hi, void* dev_slab,
+                         const void* host_slab, void* stream)
+{
+    const b200_test_info* ti = b200_get_test_info(test);
+    if (!ti || (dtype != B200_F32 && dtype != B200_F64)) { set_error("b200_load_shell_slab: bad test / dtype"); return B200_ERR_ARG; }
+    if (!dev_slab || !host_slab || nx < 0 || ny < 0 || mem_lo < 0 || mem_hi < mem_lo || mem_hi > split_n) {
+        set_error("b200_load_shell_slab: bad arguments");
+        return B200_ERR_ARG;
+    }
+    if (test == B200_MATVEC || test == B200_MATMUL || test == B200_VECADD || test == B200_SINCOS) return B200_OK;   // no shell
+    return shell_copy(ti, esz_of(dtype), nx, ny, split_n, mem_lo, mem_hi, (char*)dev_slab, (const char*)host_slab, (cudaStream_t)stream);
 }
 
 int b200_load_shell(b200_ctx* c, int slot, const void* host)

@@ -423,6 +423,11 @@ template <typename T> static int launch_tc(const HostArgs& a, int c0, int c1)
     return B200_OK;
 }
 
+// k_matmul_tc05.cu: the float GEMM on tcgen05 (TMA-fed shared-memory operands, TMEM accumulator)
+bool matmul_tc05_eligible(const float* A, const float* B, const float* C, int M, int N, int K);
+int launch_matmul_tc05(const float* A, const float* B, float* C, int M, int N, int K, int num_sms, cudaStream_t stream);
+int info_matmul_tc05(KernelInfo* ki);
+
 int launch_matmul(int dtype, const HostArgs& a)
 {
     const b200_sweep_desc& d = *a.desc;
@@ -436,11 +441,27 @@ int launch_matmul(int dtype, const HostArgs& a)
     const char* mode = getenv("B200_MATMUL");
     if (mode && !strcmp(mode, "cublas")) return launch_cublas(dtype, a, c0, c1);
 #endif
+    if (dtype == B200_F32) {
+        const float* A = (const float*)a.arrays[0];
+        const float* B = (const float*)a.arrays[1] + (size_t)c0 * d.ny;
+        float* C = (float*)a.arrays[2] + (size_t)c0 * d.nx;
+        bool tc05 = matmul_tc05_eligible(A, B, C, d.nx, c1 - c0, d.ny);
+#ifndef B200_TC05_VALIDATED      // until the chunked-accumulation form has had its GPU parity run: opt-in
+        { const char* e = getenv("B200_MATMUL_TC05"); tc05 = tc05 && e && atoi(e) != 0; }
+#endif
+#ifdef B200_DIAG
+        if (const char* e = getenv("B200_MATMUL_TC05")) tc05 = tc05 && atoi(e) != 0;     // 0: the mma.sync kernel (A/B runs)
+#endif
+        if (tc05) return launch_matmul_tc05(A, B, C, d.nx, c1 - c0, d.ny, a.num_sms, a.stream);
+    }
     return dtype == B200_F32 ? launch_tc<float>(a, c0, c1) : launch_tc<double>(a, c0, c1);
 }
 
 int info_matmul(int dtype, KernelInfo* ki)
 {
+#ifdef B200_TC05_VALIDATED
+    if (dtype == B200_F32) return info_matmul_tc05(ki);          // the kernel aligned float problems run (others: matmul_f32_kernel)
+#endif
     cudaFuncAttributes fa;
     if (dtype == B200_F32) B200_CUDA(cudaFuncGetAttributes(&fa, matmul_f32_kernel<4>));
     else B200_CUDA(cudaFuncGetAttributes(&fa, matmul_f64_kernel<2>));

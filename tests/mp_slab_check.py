@@ -69,6 +69,27 @@ def main():
                 eng.run(NT)
                 torch.cuda.synchronize()
                 mine = [eng.get_owned(q) for q in range(info["narrays"])]
+                if halo == "push" and info["exchange_slot"] >= 0:
+                    # a SECOND job on the same engine, loaded the way the end-to-end leg loads (SlabEngine.load_host: output
+                    # buffers receive only their boundary shell through b200_load_shell_slab, not even their ghost planes;
+                    # the device buffers are NaN-poisoned first): must give the same arrays again
+                    L = eng.layout
+                    host = []
+                    for q, a in enumerate(full):
+                        part = torch.from_numpy(np.ascontiguousarray(a[L.mem_lo * eng.unit:L.mem_hi * eng.unit])).pin_memory()
+                        host.append(part)
+                    for t in eng.t:
+                        t.fill_(float("nan"))
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    eng.rewind()
+                    eng.load_host(host)
+                    eng.run(NT)
+                    torch.cuda.synchronize()
+                    again = [eng.get_owned(q) for q in range(info["narrays"])]
+                    for q in range(info["narrays"]):
+                        if not np.array_equal(again[q], mine[q]):
+                            failures.append((test, real, q, "second job via load_host differs", int((again[q] != mine[q]).sum())))
                 eng.close()
             else:
                 from oracle_util import Oracle
