@@ -4,17 +4,19 @@
 //
 //   double : hand-written DGEMM on the FP64 tensor cores -- mma.sync.m8n8k4.f64 (DMMA; tcgen05 /
 //            UMMA has no FP64 kind).  CTA tile 128x128x16, 16 warps of 32x32, 4-stage cp.async ring.
-//   float  : hand-written "3xTF32" GEMM -- every operand is split in registers into a TF32 head and
-//            a TF32 tail, D += At*Bh + Ah*Bt + Ah*Bh on mma.sync.m16n8k8.tf32 with FP32 accumulate,
-//            which keeps FP32-level accuracy (the 1e-5 parity bar; a single TF32 pass does not).
-//            CTA tile 128x128x16, 8 warps of 64x32.
+//   float  : "3xTF32" -- every operand is split into a TF32 head and a TF32 tail, D += At*Bh + Ah*Bt + Ah*Bh, which keeps
+//            FP32-level accuracy (the 1e-5 parity bar; a single TF32 pass does not).  Problems TMA can address (16-byte
+//            aligned bases, nx and ny multiples of 4) run on the 5th-generation tensor cores: k_matmul_tc05.cu (tcgen05.mma
+//            kind::tf32, TMA-fed shared-memory operands, TMEM accumulators).  Everything else takes the kernel in this
+//            file: the same three products on mma.sync.m16n8k8.tf32, operands split in registers, CTA tile 128x128x16,
+//            8 warps of 64x32.
 //
 // Shared-memory tiles keep the memory order of the operands (A: m contiguous, B: k contiguous) so
 // that they are filled with 16-byte cp.async straight from the column-major arrays; the row
 // pitches are padded so that the fragment loads of a warp hit 32 distinct banks.  Extents that are
 // not multiples of the 16-byte vector (odd nx / ny) take the same kernel with element-sized
-// cp.async.  B200_MATMUL=cublas selects cuBLAS (dlopen'ed, no link dependency) as the baseline to
-// compare against; it is not the product path.
+// cp.async.  Diagnostics library only (-DB200_DIAG): B200_MATMUL=cublas selects cuBLAS (dlopen'ed) as a baseline,
+// B200_MATMUL_TC05=0 the mma.sync float kernel for aligned problems too.
 #include <dlfcn.h>
 
 #include <cstdint>
@@ -446,9 +448,6 @@ int launch_matmul(int dtype, const HostArgs& a)
         const float* B = (const float*)a.arrays[1] + (size_t)c0 * d.ny;
         float* C = (float*)a.arrays[2] + (size_t)c0 * d.nx;
         bool tc05 = matmul_tc05_eligible(A, B, C, d.nx, c1 - c0, d.ny);
-#ifndef B200_TC05_VALIDATED      // until the chunked-accumulation form has had its GPU parity run: opt-in
-        { const char* e = getenv("B200_MATMUL_TC05"); tc05 = tc05 && e && atoi(e) != 0; }
-#endif
 #ifdef B200_DIAG
         if (const char* e = getenv("B200_MATMUL_TC05")) tc05 = tc05 && atoi(e) != 0;     // 0: the mma.sync kernel (A/B runs)
 #endif
@@ -459,9 +458,7 @@ int launch_matmul(int dtype, const HostArgs& a)
 
 int info_matmul(int dtype, KernelInfo* ki)
 {
-#ifdef B200_TC05_VALIDATED
     if (dtype == B200_F32) return info_matmul_tc05(ki);          // the kernel aligned float problems run (others: matmul_f32_kernel)
-#endif
     cudaFuncAttributes fa;
     if (dtype == B200_F32) B200_CUDA(cudaFuncGetAttributes(&fa, matmul_f32_kernel<4>));
     else B200_CUDA(cudaFuncGetAttributes(&fa, matmul_f64_kernel<2>));
