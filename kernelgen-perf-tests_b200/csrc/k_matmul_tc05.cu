@@ -8,19 +8,21 @@
 // is issued as three tcgen05.mma.kind::tf32 per k-step of 8 (the At*Bt term is 2^-22 relative and dropped).
 //
 // Structure: one CTA per 128 x 128 tile of C, 6 warps with fixed roles
-//   warp 0   TMA producer: per k-block of 32, cp.async.bulk.tensor.2d of the four operand tiles (Ah, At: 4 boxes of
-//            32 m x 32 k each, M-contiguous "MN-major", 128-byte swizzle with 32-byte atoms; Bh, Bt: one box of 32 k x 128 n, "K-major", 128-byte swizzle),
-//            into a 3-stage shared-memory ring, completion on the stage's `full` mbarrier;
+//   warp 0   TMA producer: per k-block of 32, two 32 KB bulk copies (cp.async.bulk, the TMA unit's linear mode) bring the four
+//            operand tiles (Ah, At | Bh, Bt) into a 3-stage shared-memory ring, completion on the stage's `full` mbarrier.
+//            The tiles are contiguous in memory because the split pass (below) writes the operands PACKED: tile by tile, in
+//            exactly the shared-memory image the tensor core wants -- both operands "K-major": 128 rows (m or n) x 32 k,
+//            128-byte swizzle, zero-padded to whole tiles (A is transposed by the packing pass: fed m-contiguous, which for
+//            TF32 requires the 128-byte swizzle on 32-byte atoms, the MMA runs at 42 % of its rate).  (First version: tensor-map
+//            loads straight from the split arrays -- 640 requests of 128 bytes at 16 KB strides per k-block; the tensor pipe
+//            sat at 40 % waiting for them, profiles/r2_ncu_matmul_tc05.txt.)
 //   warp 1   MMA issuer: allocates 128 TMEM columns (the 128 x 128 FP32 accumulator), waits for `full`, issues
 //            4 k-steps x 3 tcgen05.mma (M = 128, N = 128, K = 8) from shared-memory descriptors, and hands the stage back
 //            with tcgen05.commit -> `empty` mbarrier; after the last k-block tcgen05.commit -> `acc_full`;
 //   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) of the accumulator, C += acc with coalesced
 //            128-byte stores (lane = row m, C is m-contiguous).
-// Out-of-range parts of edge tiles are zero-filled by the TMA unit (they add 0) and masked in the epilogue.
-// TMA needs 16-byte aligned bases and row pitches (nx, ny multiples of 4): other shapes take the mma.sync kernel of
-// k_matmul.cu.  SASS: UTCMMA / UTMALDG / LDTM / SYNCS.
-#include <cuda.h>
-
+// Out-of-range parts of edge tiles are zero in the packed operands (they add 0) and masked in the epilogue, so every shape
+// is eligible.  SASS: UTCHMMA / UBLKCP / LDTM / SYNCS.
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -45,13 +47,13 @@ constexpr int TC_TMEM_COLS = 256;                             // two 128-column 
 // chunk (other buffer) into FP32 running sums in registers with correctly rounded FADDs.
 constexpr int TC_KCHUNK_BLOCKS = 4;                           // k-blocks of 32 per chunk: 128
 
-struct alignas(64) TcMaps { CUtensorMap ah, at, bh, bt; };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
-B200_DEV void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+// linear bulk copy global -> shared through the TMA unit, completion counted in bytes on an mbarrier
+B200_DEV void tma_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 B200_DEV void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 B200_DEV void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -81,34 +83,90 @@ B200_DEV uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_
     d |= (uint64_t)layout_type << 61;                // layout_type_: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
     return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor layout): D = F32, A = B = TF32, A MN-major, B K-major
+// instruction descriptor (cute::UMMA::InstrDescriptor layout): D = F32, A = B = TF32, both operands K-major
 constexpr uint32_t tc_idesc(int m, int n)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// ---- operand split ----------------------------------------------------------------------------
+// ---- operand split + packing ------------------------------------------------------------------
 // hi = a with the 13 low mantissa bits cleared (exactly a TF32 number); lo = a - hi (exact), rounded to nearest TF32 so
 // that the tensor core's own truncation of its inputs is exact
-__global__ void __launch_bounds__(256) tc_split_kernel(const float4* __restrict__ src, float4* __restrict__ hi, float4* __restrict__ lo, size_t n4)
+B200_DEV void tc_split(float a, float& h, float& l)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = __ldcs(src + i);
-        float a[4] = { v.x, v.y, v.z, v.w }, h[4], l[4];
+    h = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+    const float t = a - h;
+    l = __uint_as_float((__float_as_uint(t) + 0x1000u) & 0xFFFFE000u);
+}
+// A (M x K, column-major, ld = M) -> packed tiles [tm][kb]{ hi 16 KB | lo 16 KB }, TRANSPOSED to "K-major": row = m, 128 bytes
+// (32 k) per row, 16-byte chunks XOR-swizzled with (m & 7)  (Swizzle<3,4,3> = SWIZZLE_128B), the same image as B's tiles.
+// (tcgen05 also accepts A m-contiguous -- "MN-major", for TF32 only with the 128-byte swizzle on 32-byte atoms -- but then the
+// MMA itself runs at 42 % of the TF32 rate: measured with the loads taken out of the loop, 139 TFLOP/s at 8192^3.)
+// One block per tile: coalesced reads along m, transpose through shared memory, coalesced 128-byte row writes.
+__global__ void __launch_bounds__(256) tc_pack_a_kernel(const float* __restrict__ A, int M, int K, unsigned char* __restrict__ ws, int mt, int nkb, int vec_ok)
+{
+    __shared__ float hi[TC_BK][TC_BM + 1], lo[TC_BK][TC_BM + 1];
+    for (int tile = blockIdx.x; tile < mt * nkb; tile += gridDim.x) {
+        const int tm = tile / nkb, kb = tile - tm * nkb;
+        const int m0 = tm * TC_BM, k0 = kb * TC_BK;
+        __syncthreads();
+        for (int e = threadIdx.x; e < TC_BK * (TC_BM / 4); e += 256) {
+            const int kk = e / (TC_BM / 4), m = 4 * (e % (TC_BM / 4));
+            float a[4] = { 0.f, 0.f, 0.f, 0.f };
+            if (k0 + kk < K) {
+                const float* src = A + (size_t)(k0 + kk) * M + m0 + m;
+                if (vec_ok && m0 + m + 3 < M) { const float4 t = __ldcs(reinterpret_cast<const float4*>(src)); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+                else {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            h[q] = __uint_as_float(__float_as_uint(a[q]) & 0xFFFFE000u);
-            const float t = a[q] - h[q];
-            l[q] = __uint_as_float((__float_as_uint(t) + 0x1000u) & 0xFFFFE000u);
+                    for (int q = 0; q < 4; q++) if (m0 + m + q < M) a[q] = src[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) tc_split(a[q], hi[kk][m + q], lo[kk][m + q]);
         }
-        hi[i] = make_float4(h[0], h[1], h[2], h[3]);
-        lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+        __syncthreads();
+        unsigned char* out = ws + (size_t)tile * (2 * TC_A_BYTES);
+        for (int e = threadIdx.x; e < TC_BM * (TC_BK / 4); e += 256) {
+            const int mm = e / (TC_BK / 4), c = e % (TC_BK / 4);           // row m, 16-byte chunk c = k / 4
+            const int chunk = c ^ (mm & 7);
+            float4 h, l;
+            h.x = hi[4 * c][mm]; h.y = hi[4 * c + 1][mm]; h.z = hi[4 * c + 2][mm]; h.w = hi[4 * c + 3][mm];
+            l.x = lo[4 * c][mm]; l.y = lo[4 * c + 1][mm]; l.z = lo[4 * c + 2][mm]; l.w = lo[4 * c + 3][mm];
+            *reinterpret_cast<float4*>(out + mm * 128 + chunk * 16) = h;
+            *reinterpret_cast<float4*>(out + TC_A_BYTES + mm * 128 + chunk * 16) = l;
+        }
+    }
+}
+// B (K x N, column-major, ld = K) -> packed tiles [tn][kb]{ hi 16 KB | lo 16 KB }: row nn = n, 128 bytes (32 k) per row,
+// 16-byte chunks XOR-swizzled with (nn & 7)  (Swizzle<3,4,3> = SWIZZLE_128B)
+__global__ void __launch_bounds__(256) tc_pack_b_kernel(const float* __restrict__ B, int K, int N, unsigned char* __restrict__ ws, int nt, int nkb, int vec_ok)
+{
+    const size_t kq = (size_t)nkb * (TC_BK / 4), total = kq * (size_t)nt * TC_BN;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (size_t)gridDim.x * blockDim.x) {
+        const int k = 4 * (int)(v % kq), n = (int)(v / kq);
+        float a[4] = { 0.f, 0.f, 0.f, 0.f };
+        if (n < N) {
+            const float* src = B + (size_t)n * K + k;
+            if (vec_ok && k + 3 < K) { const float4 t = __ldcs(reinterpret_cast<const float4*>(src)); a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w; }
+            else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (k + q < K) a[q] = src[q];
+            }
+        }
+        float h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) tc_split(a[q], h[q], l[q]);
+        const int tn = n / TC_BN, kb = k / TC_BK, nn = n % TC_BN, kk = k % TC_BK;
+        const int chunk = (kk >> 2) ^ (nn & 7);
+        unsigned char* tile = ws + ((size_t)tn * nkb + kb) * (2 * TC_B_BYTES) + nn * 128 + chunk * 16;
+        *reinterpret_cast<float4*>(tile) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(tile + TC_B_BYTES) = make_float4(l[0], l[1], l[2], l[3]);
     }
 }
 
 // ---- the GEMM ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
-matmul_tc05_kernel(const __grid_constant__ TcMaps maps, float* __restrict__ C, int M, int N, int K, int ldc, int mt)
+matmul_tc05_kernel(const unsigned char* __restrict__ wsA, const unsigned char* __restrict__ wsB, float* __restrict__ C, int M, int N, int K, int ldc, int mt)
 {
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
@@ -142,21 +200,16 @@ matmul_tc05_kernel(const __grid_constant__ TcMaps maps, float* __restrict__ C, i
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
-            tma_prefetch_desc(&maps.ah); tma_prefetch_desc(&maps.at); tma_prefetch_desc(&maps.bh); tma_prefetch_desc(&maps.bt);
+            const unsigned char* srcA = wsA + (size_t)tm * nkb * (2 * TC_A_BYTES);
+            const unsigned char* srcB = wsB + (size_t)tn * nkb * (2 * TC_B_BYTES);
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % TC_STAGES;
                 const uint32_t ph = (kb / TC_STAGES) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
                 unsigned char* st = tiles + s * TC_STAGE_BYTES;
                 mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
-                const int k0 = kb * TC_BK;
-#pragma unroll
-                for (int b = 0; b < TC_BM / 32; b++) {                  // A tiles: 4 boxes of 32 m x 32 k
-                    tma_load_2d(st + b * 4096, &maps.ah, &full[s], m0 + 32 * b, k0);
-                    tma_load_2d(st + TC_A_BYTES + b * 4096, &maps.at, &full[s], m0 + 32 * b, k0);
-                }
-                tma_load_2d(st + 2 * TC_A_BYTES, &maps.bh, &full[s], k0, n0);
-                tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &maps.bt, &full[s], k0, n0);
+                tma_bulk_load(st, srcA + (size_t)kb * (2 * TC_A_BYTES), 2 * TC_A_BYTES, &full[s]);                 // Ah | At
+                tma_bulk_load(st + 2 * TC_A_BYTES, srcB + (size_t)kb * (2 * TC_B_BYTES), 2 * TC_B_BYTES, &full[s]); // Bh | Bt
             }
         }
     } else if (warp == 1) {
@@ -178,12 +231,10 @@ matmul_tc05_kernel(const __grid_constant__ TcMaps maps, float* __restrict__ C, i
                 const uint32_t acc = tmem_acc + (uint32_t)(buf * TC_BN);
 #pragma unroll
                 for (int j = 0; j < TC_BK / 8; j++) {
-                    // A (MN-major TF32: the only legal layout is the 128-byte swizzle with 32-byte atoms, "SWIZZLE_128B_BASE32B"):
-                    // m-blocks of 32 are 4096 bytes apart (LBO), k-groups of 4 rows are 512 bytes apart (SBO); a k-step of 8
-                    // is two groups = 1024 bytes
-                    const uint64_t ah = tc_smem_desc(st + j * 1024, 4096, 512, 1u);
-                    const uint64_t at = tc_smem_desc(st + TC_A_BYTES + j * 1024, 4096, 512, 1u);
-                    // B (K-major, 128-byte swizzle): rows of 128 bytes, groups of 8 rows 1024 bytes apart (SBO); k-step = 32 bytes
+                    // A and B tiles alike (K-major, 128-byte swizzle): rows of 128 bytes (32 k), groups of 8 rows 1024 bytes apart
+                    // (SBO); a k-step of 8 = 32 bytes along the row
+                    const uint64_t ah = tc_smem_desc(st + j * 32, 16, 1024);
+                    const uint64_t at = tc_smem_desc(st + TC_A_BYTES + j * 32, 16, 1024);
                     const uint64_t bh = tc_smem_desc(st + 2 * TC_A_BYTES + j * 32, 16, 1024);
                     const uint64_t bt = tc_smem_desc(st + 2 * TC_A_BYTES + TC_B_BYTES + j * 32, 16, 1024);
                     tc_mma_tf32(acc, at, bh, idesc, (first && j == 0) ? 0u : 1u);
@@ -246,41 +297,11 @@ matmul_tc05_kernel(const __grid_constant__ TcMaps maps, float* __restrict__ C, i
 }
 
 // ---- host side --------------------------------------------------------------------------------
-typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int tc_make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
-                       uint32_t box_outer, CUtensorMapSwizzle swz)
-{
-    static tc_encode_fn enc = nullptr;
-    static std::mutex mu;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (!enc) {
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-            if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return B200_ERR_CUDA; }
-            enc = (tc_encode_fn)fn;
-        }
-    }
-    const cuuint64_t dims[2] = { inner, outer };
-    const cuuint64_t strides[1] = { pitch_elems * 4 };
-    const cuuint32_t box[2] = { box_inner, box_outer };
-    const cuuint32_t estr[2] = { 1u, 1u };
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("matmul: cuTensorMapEncodeTiled failed (%d)", (int)r); return B200_ERR_CUDA; }
-    return B200_OK;
-}
-
-// can the tcgen05 path take this problem?  (TMA: 16-byte aligned bases and pitches)
+// every float problem is eligible: the packing pass pads to whole tiles and reads unaligned operands element-wise
 bool matmul_tc05_eligible(const float* A, const float* B, const float* C, int M, int N, int K)
 {
-    (void)C;
-    return M > 0 && N > 0 && K > 0 && M % 4 == 0 && K % 4 == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
+    (void)A; (void)B; (void)C;
+    return M > 0 && N > 0 && K > 0;
 }
 
 // C (M x N, ld M) += A (M x K, ld M) * B (K x N, ld K), column-major, on `stream`
@@ -291,25 +312,18 @@ int launch_matmul_tc05(const float* A, const float* B, float* C, int M, int N, i
         B200_CUDA(cudaFuncSetAttribute(matmul_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         prepared = true;
     }
-    // split workspace, stream-ordered: Ah, At (M*K each), Bh, Bt (K*N each)
-    const size_t na = (size_t)M * K, nb = (size_t)K * N;
-    float* ws = nullptr;
-    B200_CUDA(cudaMallocAsync((void**)&ws, 2 * (na + nb) * sizeof(float), stream));
-    float *ah = ws, *at = ws + na, *bh = ws + 2 * na, *bt = ws + 2 * na + nb;
-    const int sgrid = num_sms * 8;
-    tc_split_kernel<<<sgrid, 256, 0, stream>>>((const float4*)A, (float4*)ah, (float4*)at, na / 4);
-    tc_split_kernel<<<sgrid, 256, 0, stream>>>((const float4*)B, (float4*)bh, (float4*)bt, nb / 4);
+    const int mt = (M + TC_BM - 1) / TC_BM, nt = (N + TC_BN - 1) / TC_BN, nkb = (K + TC_BK - 1) / TC_BK;
+    // packed, split operands (stream-ordered workspace): A tiles mt x nkb x 32 KB, B tiles nt x nkb x 32 KB
+    const size_t bytesA = (size_t)mt * nkb * 2 * TC_A_BYTES, bytesB = (size_t)nt * nkb * 2 * TC_B_BYTES;
+    unsigned char* ws = nullptr;
+    B200_CUDA(cudaMallocAsync((void**)&ws, bytesA + bytesB, stream));
+    const int pgrid = num_sms * 8;
+    tc_pack_a_kernel<<<(mt * nkb < pgrid * 4 ? mt * nkb : pgrid * 4), 256, 0, stream>>>(A, M, K, ws, mt, nkb, (M % 4 == 0) && ((uintptr_t)A % 16 == 0));
+    tc_pack_b_kernel<<<pgrid, 256, 0, stream>>>(B, K, N, ws + bytesA, nt, nkb, (K % 4 == 0) && ((uintptr_t)B % 16 == 0));
     B200_CUDA(cudaGetLastError());
     count_launch();
     count_launch();
-    TcMaps maps;
-    memset(&maps, 0, sizeof(maps));
-    if (int rc = tc_make_map(&maps.ah, ah, (uint64_t)M, (uint64_t)K, (uint64_t)M, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-    if (int rc = tc_make_map(&maps.at, at, (uint64_t)M, (uint64_t)K, (uint64_t)M, 32, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
-    if (int rc = tc_make_map(&maps.bh, bh, (uint64_t)K, (uint64_t)N, (uint64_t)K, TC_BK, TC_BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    if (int rc = tc_make_map(&maps.bt, bt, (uint64_t)K, (uint64_t)N, (uint64_t)K, TC_BK, TC_BN, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    const int mt = (M + TC_BM - 1) / TC_BM, nt = (N + TC_BN - 1) / TC_BN;
-    matmul_tc05_kernel<<<mt * nt, TC_THREADS, TC_SMEM_BYTES, stream>>>(maps, C, M, N, K, M, mt);
+    matmul_tc05_kernel<<<mt * nt, TC_THREADS, TC_SMEM_BYTES, stream>>>(ws, ws + bytesA, C, M, N, K, M, mt);
     B200_CUDA(cudaGetLastError());
     count_launch();
     B200_CUDA(cudaFreeAsync(ws, stream));
