@@ -306,9 +306,12 @@ def main():
     per_launch_lups = eng.local_interior_points()
     avg_launch_s = ms_total * 1e-3 / sweeps
     achieved = per_launch_lups * bytes_per_lup / avg_launch_s / 1e9
+    # DRAM bytes per launch of the same kernel from an `ncu --set full` capture (dram__bytes_read + write, committed under
+    # profiles/ by tools/collect_profiles.py; a number taken under a profiler cannot be measured inside this run).  Valid for
+    # the exact (test, precision, per-GPU grid) key and for one GPU only: slabs launch a different kernel variant -> null.
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
-    if tf.exists():
+    if tf.exists() and world == 1:
         try:
             traffic = json.loads(tf.read_text()).get(f"{test}_{real}_{nx}x{ny}x{ns}")
         except Exception:

@@ -26,6 +26,10 @@ for t in laplacian wave13pt lapgsrb uxx1 tricubic divergence; do run racecheck $
 for t in jacobi gameoflife; do run racecheck $t double 132 301 2; run synccheck $t double 132 301 2; done
 run racecheck wave13pt float 132 37 29 2
 run racecheck matmul double 130 67 140 1
+# the tcgen05 float GEMM (TMA bulk copies, mbarriers, TMEM): two tiles in n, a ragged K chunk, 2 sweeps
+run memcheck matmul float 132 300 260 2
+run racecheck matmul float 132 300 260 1
+run synccheck matmul float 132 300 260 1
 # scalar-loader path (odd pitch: no TMA)
 run memcheck laplacian double 63 31 29 2
 run racecheck laplacian double 63 31 29 2
