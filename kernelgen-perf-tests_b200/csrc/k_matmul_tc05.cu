@@ -307,10 +307,16 @@ bool matmul_tc05_eligible(const float* A, const float* B, const float* C, int M,
 // C (M x N, ld M) += A (M x K, ld M) * B (K x N, ld K), column-major, on `stream`
 int launch_matmul_tc05(const float* A, const float* B, float* C, int M, int N, int K, int num_sms, cudaStream_t stream)
 {
-    static bool prepared = false;
-    if (!prepared) {
-        B200_CUDA(cudaFuncSetAttribute(matmul_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        prepared = true;
+    {   // function attributes are per device (multi-GPU contexts launch on several)
+        static bool prepared[16] = {};
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lk(mu);
+        int dev = 0;
+        B200_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 16 && !prepared[dev]) {
+            B200_CUDA(cudaFuncSetAttribute(matmul_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+            prepared[dev] = true;
+        }
     }
     const int mt = (M + TC_BM - 1) / TC_BM, nt = (N + TC_BN - 1) / TC_BN, nkb = (K + TC_BK - 1) / TC_BK;
     // packed, split operands (stream-ordered workspace): A tiles mt x nkb x 32 KB, B tiles nt x nkb x 32 KB

@@ -4,7 +4,7 @@ O=gpurun_out/${OUT:-r2o}
 mkdir -p $O
 timeout 900 python -m pytest tests/test_gpu_multi.py "tests/test_gpu_drivers.py::test_multi_gpu_driver_matches_single" -x -q -m gpu > $O/pytest_multi.log 2>&1
 echo "pytest multi rc=$?"; tail -4 $O/pytest_multi.log
-[ -n "$DUR" ] && OUT=${OUT:-r2o}/durations bash tools/r2n_run.sh
+[ -n "$DUR" ] && OUT=${OUT:-r2o}/durations bash tools/box_runs/r2n_run.sh
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/scaling_suite.py $O/scaling_n2.json --tests laplacian,wave13pt,lapgsrb,jacobi,gaussblur,gameoflife,tricubic > /dev/null 2> $O/err_n2.txt
 python tools/scaling_suite.py $O/scaling_n1.json --tests laplacian,wave13pt,lapgsrb,jacobi,gaussblur,gameoflife,tricubic > /dev/null 2> $O/err_n1.txt
 python - <<PY
