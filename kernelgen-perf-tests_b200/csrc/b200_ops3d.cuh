@@ -187,11 +187,12 @@ template <typename T, int TYF = 24> struct DivergenceOp : NoTmaStore {
 // plane) and uz of plane s = gamma*(C_p - C_{s-1}).  ring Cq[2]: Cq[PH&1] = C_{s-1}, Cq[(PH+1)&1] = C_s.
 // The three outputs are rewritten every sweep and never read: streamed past the L2.
 // ------------------------------------------------------------------------------------------
-template <typename T, int TYF = 24> struct GradientOp : NoTmaStore {
+template <typename T, int TYF = 24, int TYD = 12, bool STREAM = true, bool PRED = true, int NCV = 384, int STG = 6> struct GradientOp : NoTmaStore {
     using real = T;
-    static constexpr int NC = pick_nc<T>(384);
-    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? TYF : 12, NC, 128), STAGES = 6, HOLD = 0, WARM = 2, PERIOD = 2;
-    static constexpr bool STREAM_OUT = true;
+    static constexpr int NC = pick_nc<T>(NCV);
+    static constexpr int TX = 128, TY = pick_ty<T>(sizeof(T) == 4 ? TYF : TYD, NC, 128), STAGES = STG, HOLD = 0, WARM = 2, PERIOD = 2;
+    static constexpr bool STREAM_OUT = STREAM;
+    static constexpr bool PRED_STORE = PRED;
     static constexpr int NSTAGED = 1;
     static constexpr StagedSpec spec(int) { return StagedSpec{0, 1, 1, 1, 1, 1}; }
 #ifdef B200_EXP_TS      // experiment build: ux, uy (plane s+1) and uz (plane s) through the TMA-store path

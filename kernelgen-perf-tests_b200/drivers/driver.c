@@ -21,7 +21,7 @@
  *
  * Extra environment: B200_NGPUS=<1..8> cuts the grid into z-slabs over that many GPUs;
  * B200_INIT_THREADS=<N> fills the host arrays with N threads in the same rand() draw order (kg_rand.h);
- * B200_PINNED_HOST=0 uses memalign instead of page-locked host arrays; B200_HBM_GBS=<GB/s> is the ceiling the
+ * B200_PINNED_HOST=0 uses memalign instead of page-locked host arrays; B200_VERIFY=1 runs the job twice and compares; B200_HBM_GBS=<GB/s> is the ceiling the
  * throughput line is compared with.  PROFILING_LINENO is accepted and unused, as in the
  * reference's cuda target (cuda_profiling.cu:21-26 stores it and never reads it).
  */
@@ -153,6 +153,12 @@ int main(int argc, char* argv[])
 	const int pinned = !(pinned_env && atoi(pinned_env) == 0);
 	volatile struct timespec t0, t1;
 	b200_ctx* ctx = NULL;
+	/* B200_VERIFY=1: self-check of the GPU path -- the whole job (load, nt sweeps, save) is run a second time on an
+	 * independent context from a copy of the inputs and must reproduce the result bit for bit: nothing in the kernels
+	 * (mbarrier rings, halo pushes and flags between GPUs, item scheduling) may depend on timing. */
+	const char* verify_env = getenv("B200_VERIFY");
+	const int verify = verify_env && atoi(verify_env) != 0;
+	real* a_copy[B200_MAX_ARRAYS] = { 0 };
 	double init_t = 0.0;
 	if (pinned)
 	{
@@ -207,6 +213,14 @@ int main(int argc, char* argv[])
 		mean = kg_fill(a, na, szarray, init_threads);
 		if (IMEAN_ALWAYS || !no_timing) printf("initial mean = %f\n", mean / szarray / na);
 	}
+
+	if (verify)
+		for (int q = 0; q < na; q++)
+		{
+			a_copy[q] = (real*)memalign(MEMALIGN, len[q] * sizeof(real) + 16);
+			if (!a_copy[q]) { printf("Error allocating memory for the B200_VERIFY copies\n"); exit(1); }
+			memcpy(a_copy[q], a[q], len[q] * sizeof(real));
+		}
 
 	/* 1) device / context initialisation  (reference: cudaGetDeviceCount probe, laplacian.c:192-199): done and timed
 	 *    above when the host arrays are page-locked (they need the context), here otherwise; reported here, where the
@@ -287,6 +301,32 @@ int main(int argc, char* argv[])
 	B200_SAFE_CALL(b200_free(ctx));
 	get_time(&t1);
 	if (!no_timing) printf("device buffer free time = %f sec\n", get_time_diff((struct timespec*)&t0, (struct timespec*)&t1));
+
+	if (verify)
+	{
+		b200_ctx* c2 = NULL;
+		b200_stats st2;
+		B200_SAFE_CALL(b200_init(&c2, 0));
+		B200_SAFE_CALL(b200_plan(c2, TEST, sizeof(real) == 4 ? B200_F32 : B200_F64, nx, ny, ns, scd, ti->nscalars));
+		B200_SAFE_CALL(b200_alloc(c2));
+		for (int q = 0; q < na; q++) B200_SAFE_CALL(b200_load(c2, q, a_copy[q]));      /* whole arrays: also checks the shell-only loads */
+		B200_SAFE_CALL(b200_run(c2, nt, &st2));
+		size_t checked = 0;
+		int bad = b200_result_slot(c2) != slot;
+		for (int q = 0; q < na && !bad; q++)
+		{
+			const int is_out = (TEST == B200_GRADIENT) ? (q >= 1 && q <= 3) : (q == slot);
+			if (!is_out) continue;
+			B200_SAFE_CALL(b200_save(c2, q, a_copy[q]));
+			if (memcmp(a_copy[q], a[q], len[q] * sizeof(real)) != 0) bad = 1;
+			checked += len[q] * sizeof(real);
+		}
+		B200_SAFE_CALL(b200_free(c2));
+		b200_destroy(c2);
+		for (int q = 0; q < na; q++) free(a_copy[q]);
+		if (bad) { fprintf(stderr, "b200 verify: FAILED -- the second run differs from the first\n"); exit(-1); }
+		printf("b200 verify: second independent run bit-identical (%zu bytes compared)\n", checked);
+	}
 
 	/* extra, unparsed by benchmark: throughput against the algorithmic byte count */
 	if (!no_timing && nt > 0 && st.kernel_ms_per_sweep > 0)

@@ -92,6 +92,17 @@ def test_pinned_host_arrays_same_result():
     assert b["t_load"] is not None and b["t_save"] is not None
 
 
+@pytest.mark.parametrize("test,dims", [("wave13pt", [130, 40, 48, 5]), ("gradient", [96, 40, 48, 2]), ("jacobi", [1024, 300, 7]),
+                                       ("tricubic", [64, 24, 40, 3]), ("matmul", [132, 64, 140, 2])])
+def test_verify_mode(test, dims):
+    """B200_VERIFY=1 (SURVEY 8b env row): the driver runs the whole job a second time on an independent context and compares
+    the results bit for bit; same stdout grammar otherwise."""
+    out = run_driver(test, "double", dims, env={"B200_VERIFY": "1"})
+    assert "b200 verify: second independent run bit-identical" in out, out
+    r = parse_like_benchmark(out, test)
+    assert r["f_mean"] is not None and r["t_comp"] is not None
+
+
 def test_readme_checksums_laplacian_wave13pt():
     """README.md:119,127 -- `./laplacian 512 256 256 10` and wave13pt, double."""
     for test, (gi, gf) in {"laplacian": (0.000041, 0.000011), "wave13pt": (0.000024, 0.000173)}.items():
