@@ -518,33 +518,49 @@ class SlabEngine:
 def e2e_slabs(eng, niters, steps, barrier, dist):
     """End to end at N > 1, one process per GPU: per step every rank uploads ITS slab of every input array from pinned
     host memory (output buffers: boundary shell only, as the C drivers and the N = 1 leg do), runs `niters` sweeps with the
-    fused halo push, and downloads its owned part of the result array.  Two engines per rank (two sets of device buffers,
-    peer mappings and flags, each on its own stream) are driven alternately, so one step's sweeps and device->host copy
-    overlap the next step's host->device copy.  Returns the dict bench.py reports."""
+    fused halo push, and downloads its owned part of the result array.  Returns the dict bench.py reports."""
+    import os
     import time
     torch = eng.torch
     pkg, info = eng.pkg, eng.info
+    # B200_E2E_PIPELINE=2: two engines per rank (two sets of device buffers, peer mappings and flags, each on its own
+    # stream) driven alternately, so that one step's copies overlap the other lane's sweeps (N = 2: 31.3 -> 36.4 GLUP/s).
+    # Default at N > 1 is ONE lane -- the caller's engine, phase by phase: the two-lane form has only been validated on 2
+    # GPUs (its first version dead-locked at N = 8, see step()).
+    depth = 2 if os.environ.get("B200_E2E_PIPELINE", "1") == "2" else 1
     lanes = []
-    for k in range(2):
-        st = torch.cuda.Stream()
-        with torch.cuda.stream(st):
-            e = SlabEngine(pkg, eng.test, eng.real, eng.nx, eng.ny if info["ndims"] == 3 else eng.ny, eng.ns, eng.scalars,
-                           world=eng.world, rank=eng.rank, dist=dist, halo=eng.halo, seed=77 + k)
+    for k in range(depth):
+        if depth == 1:
+            e, st = eng, eng.stream
+        else:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                e = SlabEngine(pkg, eng.test, eng.real, eng.nx, eng.ny, eng.ns, eng.scalars,
+                               world=eng.world, rank=eng.rank, dist=dist, halo=eng.halo, seed=77 + k)
         host = [torch.empty(e._slot_len(q), dtype=e.t[q].dtype).pin_memory() for q in range(info["narrays"])]
         for h in host:
             h.uniform_(-1, 1)
         lanes.append((e, host, st))
     L = eng.layout
     h2d = d2h = 0
+    prev_sweeps = None
 
     def step(i):
-        nonlocal h2d, d2h
-        e, host, st = lanes[i % 2]
+        nonlocal h2d, d2h, prev_sweeps
+        e, host, st = lanes[i % depth]
         st.synchronize()                      # this lane's previous step has left its host buffers
         e.rewind()
         h2d = e.load_host(host)
         with torch.cuda.stream(st):
+            # The sweeps of successive steps run in STEP ORDER on every rank (an event chain between the two lanes): the
+            # sweep kernels are persistent and spin on their neighbours' flags, so two ranks executing different lanes'
+            # sweeps at the same time would wait for each other for ever (seen at N = 8: a lane's upload finishing early on
+            # one rank let its sweeps overtake the other lane's).  Uploads and downloads still overlap the other lane's sweeps.
+            if prev_sweeps is not None:
+                st.wait_event(prev_sweeps)
             e.run(niters)
+            prev_sweeps = torch.cuda.Event()
+            prev_sweeps.record(st)
             slot = e.result_slot()
             a, b = (L.own_lo - L.mem_lo) * e.unit, (L.own_hi - L.mem_lo) * e.unit
             host[slot][a:b].copy_(e.t[slot][a:b], non_blocking=True)
@@ -555,7 +571,7 @@ def e2e_slabs(eng, niters, steps, barrier, dist):
         for _, _, st in lanes:
             st.synchronize()
 
-    for i in range(2):
+    for i in range(depth):
         step(i)
     drain()
     barrier()
@@ -573,11 +589,13 @@ def e2e_slabs(eng, niters, steps, barrier, dist):
         dt, h2d_all, d2h_all = float(mx[0].item()), int(tt[1].item()), int(tt[2].item())
     else:
         h2d_all, d2h_all = h2d, d2h
-    for e, host, st in lanes:
-        e.close()
+    if depth > 1:
+        for e, host, st in lanes:
+            e.close()
     return {"seconds_per_step": dt, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
             "api": "per-rank pinned slab copies: b200_load_shell_slab for output buffers, whole slab otherwise; b200_slab_loop "
-                   "(C ABI); two engines per rank alternating (copy/compute overlap across steps)", "steps": steps, "pipeline_depth": 2}
+                   "(C ABI)" + ("; two engines per rank alternating (copy/compute overlap across steps)" if depth > 1 else ""),
+            "steps": steps, "pipeline_depth": depth}
 
 
 def multi_eq_single(pkg, dist, test, real, nx, ny, ns, scalars, niters, world, rank, halo="push"):
