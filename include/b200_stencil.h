@@ -111,8 +111,8 @@ typedef struct {
     int out_begin, out_end;
     /* Fused halo push (multi-GPU): optional peer-mapped pointers to the lower /
      * upper neighbour's copy of the OUTPUT array (same layout, the neighbour's
-     * local coordinates).  The kernel stores the planes the neighbour needs as
-     * ghosts directly into peer memory over NVLink while it computes.
+     * local coordinates).  The kernel copies the planes the neighbour needs as
+     * ghosts directly into peer memory over NVLink while the rest of the grid is still being swept.
      * push_lo_dst_plane: first ghost plane index in the lower neighbour that
      * receives our planes [push_lo_src_plane, +zghost_hi); likewise for hi. */
     void* push_lo; int push_lo_src_plane; int push_lo_dst_plane; int push_lo_count;
@@ -120,10 +120,13 @@ typedef struct {
     /* 1: walk the work items back to front.  Alternating 0/1 between consecutive sweeps makes a
      * sweep start on the data its predecessor touched last, which is still in L2. */
     int reverse_order;
-    /* Ordering between neighbour ranks, done INSIDE the sweep kernel (only with push_lo/push_hi):
-     * before touching any data the kernel spins until *wait_flag[i] >= wait_value (acquire, system
-     * scope; NULL = no wait), and when the last CTA has finished it stores signal_value to
-     * signal_flag[i] (release, system scope; normally a flag in the neighbour's memory). */
+    /* Ordering between neighbour ranks, done INSIDE the sweep kernel (only with push_lo/push_hi).  A pushing launch
+     * walks the END units of the split dimension first (the z-chunks / tile rows that read a ghost plane or produce a
+     * plane a neighbour needs); before a CTA loads its first such item it spins until *wait_flag[i] >= wait_value
+     * (acquire, system scope; NULL = no wait), every finished end item copies its share of the ghost planes into the
+     * neighbours' arrays, and when the last end item of the grid has done so signal_value is stored to signal_flag[i]
+     * (release, system scope; normally a flag in the neighbour's memory) -- early in the sweep; interior items take no
+     * part in the ordering. */
     const void* wait_flag[2];
     unsigned long long wait_value;
     void* signal_flag[2];
@@ -206,8 +209,9 @@ int b200_load_shell(b200_ctx* ctx, int slot, const void* host);
 int b200_run(b200_ctx* ctx, int niters, b200_stats* stats);
 int b200_result_slot(const b200_ctx* ctx);          /* slot (original numbering) the reference reports f_mean on */
 int b200_save(b200_ctx* ctx, int slot, void* host);
-/* Asynchronous mode (new: the reference's drivers synchronise after every phase, laplacian.c:255-262,303-305,
- * 334-340).  With b200_set_async(ctx, 1) the phase calls b200_load / b200_load_shell / b200_run / b200_save only
+/* Asynchronous mode, SINGLE-GPU contexts only (b200_set_async(ctx, 1) on a multi-GPU context returns B200_ERR_STATE: there
+ * the ordering between neighbouring slabs' loads, halo pushes and saves relies on the synchronisation this mode removes).
+ * New: the reference's drivers synchronise after every phase, laplacian.c:255-262,303-305, 334-340.  With b200_set_async(ctx, 1) the phase calls b200_load / b200_load_shell / b200_run / b200_save only
  * ENQUEUE their copies and sweeps on the context's own streams and return; b200_sync(ctx) waits for all of it.
  * Host arrays must be pinned (b200_host_alloc) and stay untouched until b200_sync; b200_run fills no times
  * (stats: launches, regs, name only).  Two contexts driven alternately overlap one job's device->host copy and

@@ -9,13 +9,14 @@
 //     every staged input (with its x/y halo) into a shared-memory ring with
 //     TMA (cp.async.bulk.tensor.3d + mbarrier complete_tx); out-of-range
 //     halo is zero-filled by the TMA unit;
-//   * 8 consumer warps wait on the stage's "full" mbarrier, run Op::step()
+//   * 8 - 16 consumer warps (Op::NC) wait on the stage's "full" mbarrier, run Op::step()
 //     -- the stencil proper: in-plane neighbours from shared memory with
 //     16-byte loads, z neighbours from per-thread register queues (2.5D
 //     z-march) -- store results with 16-byte coalesced stores and hand the
 //     stage back through the "empty" mbarrier;
-//   * optional fused halo push: planes a z-neighbour GPU needs as ghosts are
-//     also stored straight into that GPU's memory (peer pointer over NVLink).
+//   * optional fused halo push (PUSH launches): the items that touch the slab's ends are walked first, each finished
+//     one copies the planes a z-neighbour GPU needs as ghosts straight into that GPU's memory (peer pointer over
+//     NVLink), and the neighbour ordering (flags) involves only those items.
 //
 // When a row pitch is not a multiple of 16 bytes TMA cannot be used; the
 // producer warp then fills the same ring with bounds-checked scalar loads.
