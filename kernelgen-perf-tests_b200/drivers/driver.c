@@ -168,17 +168,17 @@ int main(int argc, char* argv[])
 		init_t = get_time_diff((struct timespec*)&t0, (struct timespec*)&t1);
 	}
 	real* a[B200_MAX_ARRAYS] = { 0 };
+	int a_pinned[B200_MAX_ARRAYS] = { 0 };
 	int ok = 1;
 	for (int q = 0; q < na; q++)
 	{
 		if (pinned)
 		{
+			/* page-locking tens of GB can be refused (locked-memory limits): such an array falls back to memalign */
 			void* ptr = NULL;
-			if (b200_host_alloc(&ptr, len[q] * sizeof(real) + 16) != B200_OK) ptr = NULL;
-			a[q] = (real*)ptr;
+			if (b200_host_alloc(&ptr, len[q] * sizeof(real) + 16) == B200_OK && ptr) { a[q] = (real*)ptr; a_pinned[q] = 1; }
 		}
-		else
-			a[q] = (real*)memalign(MEMALIGN, len[q] * sizeof(real) + 16);
+		if (!a[q]) a[q] = (real*)memalign(MEMALIGN, len[q] * sizeof(real) + 16);
 		if (!a[q]) ok = 0;
 	}
 	if (!ok)
@@ -378,7 +378,7 @@ int main(int argc, char* argv[])
 	b200_destroy(ctx);
 	for (int q = 0; q < na; q++)
 	{
-		if (pinned) b200_host_free(a[q]);
+		if (a_pinned[q]) b200_host_free(a[q]);
 		else free(a[q]);
 	}
 	fflush(stdout);
