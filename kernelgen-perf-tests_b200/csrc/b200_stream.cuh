@@ -603,6 +603,9 @@ stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ Te
                                 }
                             }
                         }
+                        // the ghost planes were written by the neighbours' generic-proxy stores; this lane reads them through
+                        // the async proxy (TMA) next
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
                     __syncwarp(P.use_tma ? 1u : 0xffffffffu);
                     ordered = true;
