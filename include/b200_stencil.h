@@ -212,7 +212,10 @@ int b200_save(b200_ctx* ctx, int slot, void* host);
 /* Asynchronous mode, SINGLE-GPU contexts only (b200_set_async(ctx, 1) on a multi-GPU context returns B200_ERR_STATE: there
  * the ordering between neighbouring slabs' loads, halo pushes and saves relies on the synchronisation this mode removes).
  * New: the reference's drivers synchronise after every phase, laplacian.c:255-262,303-305, 334-340.  With b200_set_async(ctx, 1) the phase calls b200_load / b200_load_shell / b200_run / b200_save only
- * ENQUEUE their copies and sweeps on the context's own streams and return; b200_sync(ctx) waits for all of it.
+ * ENQUEUE their copies and sweeps and return; b200_sync(ctx) waits for all of it.  The sweeps run on the context's own
+ * stream; the copies of all asynchronous contexts of a device run on two shared streams, one per direction, each copy
+ * ordered after everything the context enqueued before it and before everything it enqueues next (copies left on the
+ * contexts' own streams did not overlap across contexts: profiles/r2_e2e_pipeline.txt; B200_COPY_STREAMS=0 puts them back).
  * Host arrays must be pinned (b200_host_alloc) and stay untouched until b200_sync; b200_run fills no times
  * (stats: launches, regs, name only).  Two contexts driven alternately overlap one job's device->host copy and
  * sweeps with the next job's host->device copy (PCIe is full duplex): that is how bench.py's e2e leg and a
