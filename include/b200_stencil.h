@@ -152,7 +152,8 @@ int b200_sweep_loop(const b200_sweep_desc* desc, void** arrays, int niters, void
  * Replaces two iterations of the nt-loop (e.g. gameoflife/gameoflife.c:276-289).  Single GPU. */
 int b200_sweep2_supported(int test);
 /* 1 when b200_run / b200_sweep_loop2 would use the fused kernel for this test and row length (a measured
- * policy: today jacobi with nx >= 1024; B200_FUSE=1 / 0 forces it on / off). */
+ * policy: today jacobi with nx >= 1024; B200_FUSE=1 / 0 forces it on / off, as does B200_TBLOCK=2 / 1,
+ * the number of sweeps per pass). */
 int b200_sweep2_profitable(int test, int nx);
 int b200_sweep2(const b200_sweep_desc* desc, void* const* arrays, void* stream);
 

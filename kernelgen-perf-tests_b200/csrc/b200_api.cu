@@ -289,6 +289,8 @@ static launch_fn fused_launch(int test, int nx)
 {
     const char* e = getenv("B200_FUSE");           // read per call: tests toggle it
     if (e) return atoi(e) ? fused_kernel(test) : nullptr;
+    // B200_TBLOCK=<sweeps per pass> (env row): 1 = one sweep per pass, 2 = the two-sweep kernels wherever they exist
+    if (const char* tb = getenv("B200_TBLOCK")) return atoi(tb) >= 2 ? fused_kernel(test) : nullptr;
     return (test == B200_JACOBI && nx >= 1024) ? fused_kernel(test) : nullptr;
 }
 
